@@ -1,0 +1,62 @@
+// Shared declarations for libbore_b200.so (sm_100a).  See include/bore_b200.h for the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/bore_b200.h"
+
+// ---------------------------------------------------------------- error plumbing
+void bore_set_error(const char *fmt, ...);
+
+#define BORE_CHECK(cond, ...)            \
+  do {                                   \
+    if (!(cond)) {                       \
+      bore_set_error(__VA_ARGS__);       \
+      return -1;                         \
+    }                                    \
+  } while (0)
+
+#define BORE_CUDA(call)                                                          \
+  do {                                                                           \
+    cudaError_t e__ = (call);                                                    \
+    if (e__ != cudaSuccess) {                                                    \
+      bore_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,               \
+                     cudaGetErrorString(e__));                                   \
+      return -2;                                                                 \
+    }                                                                            \
+  } while (0)
+
+// ---------------------------------------------------------------- model descriptor
+// Passed by value to kernels (lives in kernel parameter space / constant bank).
+struct MlpDesc {
+  int n_layers;                     // Dense layers incl. the final (out_dim 1) layer
+  int dims[BORE_MAX_LAYERS + 1];    // dims[0] = D
+  int act[BORE_MAX_LAYERS];
+  int w_off[BORE_MAX_LAYERS];       // offsets into the flat Keras-order parameter vector
+  int b_off[BORE_MAX_LAYERS];
+  int n_params;
+};
+
+struct bore_mlp {
+  MlpDesc desc;
+  int n_models;
+  int device;
+  int sm_count;
+  float *params;       // [n_models][n_params]
+  float *adam_m;       // [n_models][n_params]
+  float *adam_v;       // [n_models][n_params]
+  long long *adam_t;   // [n_models]   Keras `iterations`
+};
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// ---------------------------------------------------------------- launchers (one per .cu)
+// K0 / K2.  `list` (may be NULL) is a device array of row indices: point i of the launch
+// is row list[i] of X / f / g (used by the L-BFGS-B driver's compacted active list);
+// `n_dev` (may be NULL) is a device int holding the number of points (<= S).
+int launch_mlp_eval(const bore_mlp *h, int model, bool want_grad, int transform, int negate,
+                    const float *X, int S, float *f, float *g, const int *list,
+                    const int *n_dev, cudaStream_t stream);

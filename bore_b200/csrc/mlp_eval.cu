@@ -1,0 +1,349 @@
+// K0 / K2: batched MLP forward and fused forward + reverse-through-input (sm_100a, FP32 FFMA).
+//
+// Replaces, for S points at once, what the reference evaluates one point per TensorFlow
+// dispatch: keras predict (bore/mixins.py:50) and the value_and_gradient closure of
+// convert() (bore/base.py:35-42, bore/decorators.py:48-65) with transform(-u)
+// (bore/mixins.py:20).
+//
+// Mapping.  Weights (forward layout W[k][j] and, for the reverse pass, the transposed
+// layout WT[j][k]) are staged once per CTA into shared memory, zero-padded so that every
+// inner loop is branch-free.  Each WARP owns tiles of 16 points and carries them through
+// all layers on its own: activations live in a per-warp shared-memory strip laid out
+// [unit][point] (row stride 20 floats), so layers hand over with __syncwarp only -- no CTA
+// barrier after the weight load.  Inside a tile every lane owns a 4-point x 4-unit
+// register block: lane = pg*8 + ug, points pg*4..+3, units chunk*32 + ug*4..+3.  One k-step
+// is two LDS.128 (4 activations, 4 weights) feeding 16 FFMA, so the loop is FFMA-issue
+// bound, not shared-memory bound.  The reverse pass reuses the same loop on WT and
+// multiplies by act'(h) (expressed through the stored layer output, as TF's *Grad kernels
+// do) in the epilogue, overwriting the activation strip in place.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TP = 16;   // points per warp tile
+constexpr int AST = 20;  // activation strip row stride (floats): conflict-free float4 rows
+
+__device__ __forceinline__ float act_fwd(int a, float v) {
+  switch (a) {
+    case BORE_ACT_RELU: return fmaxf(v, 0.f);
+    case BORE_ACT_ELU: return v > 0.f ? v : expm1f(v);
+    case BORE_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    case BORE_ACT_TANH: return tanhf(v);
+    default: return v;
+  }
+}
+// derivative wrt the pre-activation, through the layer OUTPUT h
+__device__ __forceinline__ float act_bwd(int a, float h) {
+  switch (a) {
+    case BORE_ACT_RELU: return h > 0.f ? 1.f : 0.f;
+    case BORE_ACT_ELU: return h > 0.f ? 1.f : h + 1.f;
+    case BORE_ACT_SIGMOID: return h * (1.f - h);
+    case BORE_ACT_TANH: return 1.f - h * h;
+    default: return 1.f;
+  }
+}
+
+struct SmemPlan {
+  int wf[BORE_MAX_LAYERS];   // forward weights  [in4][outP]
+  int wb[BORE_MAX_LAYERS];   // reverse weights  [out4][inP]
+  int bias[BORE_MAX_LAYERS]; // [outP]
+  int wl;                    // final layer vector, padded
+  int weights_total;         // floats
+  int buf[BORE_MAX_LAYERS];  // per-warp strip offsets (floats, relative to the warp's base)
+  int warp_total;            // floats per warp
+  int wl_len;
+};
+
+__host__ __device__ inline int rup(int a, int b) { return (a + b - 1) / b * b; }
+
+__host__ __device__ inline void make_plan(const MlpDesc &d, bool grad, SmemPlan &p) {
+  int off = 0;
+  const int G = d.n_layers - 1;  // GEMM (hidden) layers
+  for (int l = 0; l < G; ++l) {
+    int in = d.dims[l], out = d.dims[l + 1];
+    p.wf[l] = off; off += rup(in, 4) * rup(out, 32);
+    p.bias[l] = off; off += rup(out, 32);
+    p.wb[l] = off; if (grad) off += rup(out, 4) * rup(in, 32);
+  }
+  p.wl_len = G > 0 ? rup(d.dims[G], 32) : rup(d.dims[0], 8);
+  p.wl = off; off += p.wl_len;
+  p.weights_total = rup(off, 4);
+  int w = 0;
+  p.buf[0] = 0; w += AST * (G > 0 ? rup(d.dims[0], 4) : rup(d.dims[0], 8));
+  for (int l = 1; l <= G; ++l) { p.buf[l] = w; w += AST * rup(d.dims[l], 32); }
+  p.warp_total = w;
+}
+
+// acc[i][u] += sum_k A[k][pg*4+i] * W[k][col0+u],  k < K4 (multiple of 4)
+__device__ __forceinline__ void tile_gemm(const float *__restrict__ A, const float *__restrict__ W,
+                                          int K4, int ldw, float (&acc)[4][4]) {
+#pragma unroll 2
+  for (int k = 0; k < K4; k += 4) {
+    float4 a[4], w[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      a[kk] = *reinterpret_cast<const float4 *>(A + (k + kk) * AST);
+      w[kk] = *reinterpret_cast<const float4 *>(W + (k + kk) * ldw);
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float av[4] = {a[kk].x, a[kk].y, a[kk].z, a[kk].w};
+      const float wv[4] = {w[kk].x, w[kk].y, w[kk].z, w[kk].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[i][u] = fmaf(av[i], wv[u], acc[i][u]);
+    }
+  }
+}
+
+template <bool GRAD>
+__global__ void __launch_bounds__(512)
+mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ params,
+                const float *__restrict__ X,
+                int S, const int *__restrict__ n_dev, const int *__restrict__ list,
+                float *__restrict__ f_out, float *__restrict__ g_out, int transform, float sign) {
+  extern __shared__ __align__(16) float smem[];
+  const int G = d.n_layers - 1;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+
+  // ---- stage weights (zero padded) ----
+  for (int l = 0; l < G; ++l) {
+    const int in = d.dims[l], out = d.dims[l + 1];
+    const int in4 = rup(in, 4), outP = rup(out, 32);
+    const float *Wg = params + d.w_off[l];
+    float *wf = smem + P.wf[l];
+    for (int e = tid; e < in4 * outP; e += nthr) {
+      int k = e / outP, j = e - k * outP;
+      wf[e] = (k < in && j < out) ? Wg[k * out + j] : 0.f;
+    }
+    float *bs = smem + P.bias[l];
+    for (int e = tid; e < outP; e += nthr) bs[e] = e < out ? params[d.b_off[l] + e] : 0.f;
+    if (GRAD) {
+      const int out4 = rup(out, 4), inP = rup(in, 32);
+      float *wb = smem + P.wb[l];
+      for (int e = tid; e < out4 * inP; e += nthr) {
+        int j = e / inP, k = e - j * inP;
+        wb[e] = (k < in && j < out) ? Wg[k * out + j] : 0.f;
+      }
+    }
+  }
+  {
+    const int in = d.dims[G];
+    float *wl = smem + P.wl;
+    for (int e = tid; e < P.wl_len; e += nthr) wl[e] = e < in ? params[d.w_off[G] + e] : 0.f;
+  }
+  const float b_last = params[d.b_off[G]];
+  const int act_last = d.act[G];
+  __syncthreads();
+
+  const int n = n_dev ? min(*n_dev, S) : S;
+  const int n_tiles = (n + TP - 1) / TP;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+  const int ug = lane & 7, pg = lane >> 3;
+  float *strip = smem + P.weights_total + warp * P.warp_total;
+  const int D = d.dims[0];
+  const float *wl = smem + P.wl;
+
+  for (int tile = blockIdx.x * nwarps + warp; tile < n_tiles; tile += gridDim.x * nwarps) {
+    const int p0 = tile * TP;
+    // ---- load the 16 input rows, transposed into buf0[k][p] ----
+    {
+      float *xb = strip + P.buf[0];
+      const int rows0 = G > 0 ? rup(D, 4) : rup(D, 8);
+      for (int pl = 0; pl < TP; ++pl) {
+        const int idx = p0 + pl;
+        const bool ok = idx < n;
+        const long row = ok ? (list ? list[idx] : idx) : 0;
+        for (int k = lane; k < rows0; k += 32)
+          xb[k * AST + pl] = (ok && k < D) ? X[row * D + k] : 0.f;
+      }
+    }
+    __syncwarp();
+
+    // ---- forward through the hidden layers ----
+    for (int l = 0; l < G; ++l) {
+      const int in4 = rup(d.dims[l], 4), outP = rup(d.dims[l + 1], 32);
+      const float *A = strip + P.buf[l] + pg * 4;
+      float *H = strip + P.buf[l + 1];
+      const float *W = smem + P.wf[l];
+      const float *bs = smem + P.bias[l];
+      const int a = d.act[l];
+      for (int c = 0; c < outP; c += 32) {
+        float acc[4][4] = {};
+        tile_gemm(A, W + c + ug * 4, in4, outP, acc);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int unit = c + ug * 4 + u;
+          const float b = bs[unit];
+          float4 o;
+          o.x = act_fwd(a, acc[0][u] + b);
+          o.y = act_fwd(a, acc[1][u] + b);
+          o.z = act_fwd(a, acc[2][u] + b);
+          o.w = act_fwd(a, acc[3][u] + b);
+          *reinterpret_cast<float4 *>(H + unit * AST + pg * 4) = o;
+        }
+      }
+      __syncwarp();
+    }
+
+    // ---- final Dense(1): u = act(h . w + b) for this lane's 4 points ----
+    float *HL = strip + P.buf[G];
+    float up[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = ug; k < P.wl_len; k += 8) {
+      const float4 hv = *reinterpret_cast<const float4 *>(HL + k * AST + pg * 4);
+      const float w = wl[k];
+      up[0] = fmaf(hv.x, w, up[0]);
+      up[1] = fmaf(hv.y, w, up[1]);
+      up[2] = fmaf(hv.z, w, up[2]);
+      up[3] = fmaf(hv.w, w, up[3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      up[i] += __shfl_xor_sync(0xffffffffu, up[i], 1);
+      up[i] += __shfl_xor_sync(0xffffffffu, up[i], 2);
+      up[i] += __shfl_xor_sync(0xffffffffu, up[i], 4);
+    }
+    float dpre[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float u = act_fwd(act_last, up[i] + b_last);
+      float fval, dT;
+      if (GRAD) {
+        const float v = sign * u;
+        if (transform == BORE_TRANSFORM_SIGMOID) {
+          fval = 1.f / (1.f + expf(-v));
+          dT = fval * (1.f - fval);
+        } else if (transform == BORE_TRANSFORM_EXP) {
+          fval = expf(v);
+          dT = fval;
+        } else {
+          fval = v;
+          dT = 1.f;
+        }
+        dpre[i] = dT * sign * act_bwd(act_last, u);
+      } else {
+        fval = u;
+      }
+      const int idx = p0 + pg * 4 + i;
+      if (ug == 0 && idx < n) f_out[list ? list[idx] : idx] = fval;
+    }
+    if (!GRAD) { __syncwarp(); continue; }
+
+    // ---- reverse: delta of the last hidden layer (elementwise), then GEMMs on WT ----
+    if (G == 0) {
+      // no hidden layer: g = dpre * w
+      for (int k = ug; k < D; k += 8) {
+        const float w = wl[k];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int idx = p0 + pg * 4 + i;
+          if (idx < n) g_out[(long)(list ? list[idx] : idx) * D + k] = dpre[i] * w;
+        }
+      }
+      __syncwarp();
+      continue;
+    }
+    {
+      const int a = d.act[G - 1];
+      for (int k = ug; k < P.wl_len; k += 8) {
+        float4 hv = *reinterpret_cast<const float4 *>(HL + k * AST + pg * 4);
+        const float w = wl[k];
+        hv.x = dpre[0] * w * act_bwd(a, hv.x);
+        hv.y = dpre[1] * w * act_bwd(a, hv.y);
+        hv.z = dpre[2] * w * act_bwd(a, hv.z);
+        hv.w = dpre[3] * w * act_bwd(a, hv.w);
+        *reinterpret_cast<float4 *>(HL + k * AST + pg * 4) = hv;
+      }
+    }
+    __syncwarp();
+    for (int l = G - 1; l >= 0; --l) {
+      const int out4 = rup(d.dims[l + 1], 4), inP = rup(d.dims[l], 32);
+      const float *A = strip + P.buf[l + 1] + pg * 4;   // delta_out [j][p]
+      const float *W = smem + P.wb[l];                  // WT [j][k]
+      float *Hin = strip + P.buf[l];
+      if (l > 0) {
+        const int a = d.act[l - 1];
+        for (int c = 0; c < inP; c += 32) {
+          float acc[4][4] = {};
+          tile_gemm(A, W + c + ug * 4, out4, inP, acc);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float *hp = Hin + (c + ug * 4 + u) * AST + pg * 4;
+            float4 hv = *reinterpret_cast<const float4 *>(hp);
+            hv.x = acc[0][u] * act_bwd(a, hv.x);
+            hv.y = acc[1][u] * act_bwd(a, hv.y);
+            hv.z = acc[2][u] * act_bwd(a, hv.z);
+            hv.w = acc[3][u] * act_bwd(a, hv.w);
+            *reinterpret_cast<float4 *>(hp) = hv;
+          }
+        }
+        __syncwarp();
+      } else {
+        // input gradient: stage through buf0 (x is dead) so the global store is coalesced
+        for (int c = 0; c < inP; c += 32) {
+          float acc[4][4] = {};
+          tile_gemm(A, W + c + ug * 4, out4, inP, acc);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int k = c + ug * 4 + u;
+            if (k < rup(D, 4))
+              *reinterpret_cast<float4 *>(Hin + k * AST + pg * 4) =
+                  make_float4(acc[0][u], acc[1][u], acc[2][u], acc[3][u]);
+          }
+        }
+        __syncwarp();
+        for (int pl = 0; pl < TP; ++pl) {
+          const int idx = p0 + pl;
+          if (idx >= n) break;
+          const long row = list ? list[idx] : idx;
+          for (int k = lane; k < D; k += 32) g_out[row * D + k] = Hin[k * AST + pl];
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+}  // namespace
+
+int launch_mlp_eval(const bore_mlp *h, int model, bool want_grad, int transform, int negate,
+                    const float *X, int S, float *f, float *g, const int *list,
+                    const int *n_dev, cudaStream_t stream) {
+  if (S <= 0) return 0;
+  const MlpDesc &d = h->desc;
+  SmemPlan P;
+  make_plan(d, want_grad, P);
+  const int max_smem = 227 * 1024;
+  // warps per CTA: as many as fit (<= 16), at least 1
+  int warps = 16;
+  while (warps > 1 &&
+         (size_t)(P.weights_total + warps * P.warp_total) * sizeof(float) > (size_t)max_smem)
+    --warps;
+  const size_t smem = (size_t)(P.weights_total + warps * P.warp_total) * sizeof(float);
+  BORE_CHECK(smem <= (size_t)max_smem, "mlp_eval: model needs %zu B of shared memory (> %d)",
+             smem, max_smem);
+  const int n_tiles = (S + TP - 1) / TP;
+  int ctas_needed = (n_tiles + warps - 1) / warps;
+  int per_sm = (int)((size_t)max_smem / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm * warps > 48) per_sm = 48 / warps > 0 ? 48 / warps : 1;
+  int grid = h->sm_count * per_sm;
+  if (grid > ctas_needed) grid = ctas_needed;
+  if (grid < 1) grid = 1;
+  const float *params = h->params + (size_t)model * d.n_params;
+  const float sign = negate ? -1.f : 1.f;
+  if (want_grad) {
+    BORE_CUDA(cudaFuncSetAttribute(mlp_eval_kernel<true>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_eval_kernel<true><<<grid, warps * 32, smem, stream>>>(d, P, params, X, S, n_dev, list, f, g,
+                                                             transform, sign);
+  } else {
+    BORE_CUDA(cudaFuncSetAttribute(mlp_eval_kernel<false>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_eval_kernel<false><<<grid, warps * 32, smem, stream>>>(d, P, params, X, S, n_dev, list, f, g,
+                                                              transform, sign);
+  }
+  BORE_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,181 @@
+/*
+ * bore_b200.h -- C ABI of libbore_b200.so: the B200-native (sm_100a) replacement for the
+ * third-party numerics underneath ltiao/bore's BORE-MLP hot path.
+ *
+ * The reference (pure Python, /root/reference) has no FFI of its own; everything below
+ * replaces a *library call site* in it.  Each entry point cites the reference call it
+ * stands in for.  The only caller is the Python host layer `bore_b200/_lib.py` (ctypes).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; bore_last_error() gives the text
+ *     (thread-local).
+ *   - `*_dev` pointers are device pointers owned by the caller (e.g. torch `data_ptr()`);
+ *     `*_host` pointers are host pointers.  No torch types cross this boundary.
+ *   - `stream` is a `cudaStream_t` passed as void* (NULL = legacy default stream).
+ *     Kernels are enqueued on it; functions do not synchronise unless documented.
+ *   - handles are not thread-affine: every call sets the CUDA device of its handle
+ *     (HpBandSter calls get_config / new_result from different threads,
+ *     bore/plugins/hpbandster/base.py:216,276).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef BORE_B200_H
+#define BORE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BORE_ABI_VERSION 1
+
+/* activations of a Dense layer (Keras names: linear, relu, elu, sigmoid, tanh) */
+enum { BORE_ACT_LINEAR = 0, BORE_ACT_RELU = 1, BORE_ACT_ELU = 2, BORE_ACT_SIGMOID = 3,
+       BORE_ACT_TANH = 4 };
+/* output transforms, TRANSFORMS of bore/plugins/hpbandster/base.py:18 */
+enum { BORE_TRANSFORM_IDENTITY = 0, BORE_TRANSFORM_SIGMOID = 1, BORE_TRANSFORM_EXP = 2 };
+/* per-start termination status, scipy.optimize.OptimizeResult.status for L-BFGS-B */
+enum { BORE_STATUS_CONVERGED = 0, BORE_STATUS_LIMIT = 1, BORE_STATUS_ABNORMAL = 2 };
+
+#define BORE_MAX_LAYERS 8     /* Dense layers per model, final layer included */
+#define BORE_MAX_WIDTH 128    /* widest hidden layer */
+#define BORE_MAX_DIM 512      /* input dimension */
+#define BORE_LBFGSB_MAXCOR 10 /* upper limit of the `m` (maxcor) option */
+
+typedef struct bore_mlp bore_mlp; /* opaque: M independent MLPs of one architecture */
+
+int bore_abi_version(void);
+const char *bore_last_error(void);
+/* number of visible CUDA devices (0 => every compute call will fail) */
+int bore_device_count(void);
+
+/* ---- model container ---------------------------------------------------------------
+ * Replaces keras.Sequential + Dense as built at README.rst:60-64, bore/models.py:9-21.
+ * dims[0..n_layers] = input dim, hidden widths..., output dim (must be 1);
+ * acts[0..n_layers-1] = BORE_ACT_*.  n_models independent weight sets (seeds / BO
+ * problems / per-budget classifiers) share the architecture.  Parameters are fp32 in
+ * Keras get_weights() order: [W0 (in,out) row-major, b0, W1, b1, ...], flat.           */
+int bore_mlp_create(int n_layers, const int *dims, const int *acts, int n_models,
+                    int device, bore_mlp **out);
+int bore_mlp_destroy(bore_mlp *h);
+int bore_mlp_num_params(const bore_mlp *h);
+int bore_mlp_num_models(const bore_mlp *h);
+/* keras Model.set_weights / get_weights (host buffers, n_params floats); synchronous */
+int bore_mlp_set_weights(bore_mlp *h, int model, const float *params_host);
+int bore_mlp_get_weights(bore_mlp *h, int model, float *params_host);
+/* Adam slots m, v (n_params floats each) and the step counter `iterations`; Keras keeps
+ * them alive across fit() calls on one model (README.rst:93 loop).  synchronous        */
+int bore_mlp_set_adam_state(bore_mlp *h, int model, const float *m_host,
+                            const float *v_host, int64_t iterations);
+int bore_mlp_get_adam_state(bore_mlp *h, int model, float *m_host, float *v_host,
+                            int64_t *iterations);
+/* device pointer of the flat parameter block [n_models][n_params] (for NCCL broadcast) */
+int bore_mlp_params_dev(bore_mlp *h, float **params_dev);
+
+/* ---- K0: batched forward -------------------------------------------------------------
+ * Replaces keras Model.predict at bore/mixins.py:50.  X_dev [S][D] fp32 row-major,
+ * out_dev [S] fp32 (model output, final activation applied).                            */
+int bore_mlp_predict(bore_mlp *h, int model, const float *X_dev, int S, float *out_dev,
+                     void *stream);
+
+/* ---- K2: fused value + input-gradient --------------------------------------------------
+ * Replaces the tf.function/GradientTape closure built by convert()
+ * (bore/base.py:35-42, bore/decorators.py:48-65): f = T(sign*u(x)), g = df/dx with
+ * sign = -1 when negate!=0 (the `_func_min` of bore/mixins.py:20), +1 otherwise
+ * (`_func_max`, bore/mixins.py:97).  X_dev [S][D], f_dev [S], g_dev [S][D], all fp32.   */
+int bore_mlp_value_and_grad(bore_mlp *h, int model, int transform, int negate,
+                            const float *X_dev, int S, float *f_dev, float *g_dev,
+                            void *stream);
+
+/* ---- K1: fused training ----------------------------------------------------------------
+ * Replaces keras Model.fit(X, z, epochs, batch_size, shuffle=True) compiled with adam +
+ * binary cross-entropy (README.rst:66,93; bore/plugins/hpbandster/base.py:156-157,184):
+ * the whole run is one launch, one CTA group per model.  Models [model0, model0+count)
+ * train concurrently, model j on rows [j*N, (j+1)*N) of X_dev/z_dev when
+ * `shared_data == 0`, or all on the same N rows when `shared_data != 0`.
+ *   X_dev [*][D] fp32, z_dev [*] fp32 (0/1 labels)
+ *   perm_dev [count or 1][epochs][N] int32: the per-epoch shuffles (Keras draws them
+ *     internally; made explicit so trajectories can be compared).  One set per model, or
+ *     one shared set when `shared_perm != 0`.
+ *   l2: weight of the l2(kernel)+l2(bias) regulariser (plugins/hpbandster/base.py:113-116)
+ *   loss_out_dev [count][epochs] fp32: Keras' history["loss"] (sample-weighted running
+ *     mean of the per-batch losses, each taken before its update); may be NULL.
+ * Weights and Adam state of the handle are updated in place.                            */
+int bore_mlp_fit(bore_mlp *h, int model0, int count, const float *X_dev,
+                 const float *z_dev, int N, int shared_data, int batch_size, int epochs,
+                 const int32_t *perm_dev, int shared_perm, float l2, float *loss_out_dev,
+                 void *stream);
+
+/* Keras Model.evaluate -> mean loss and `accuracy` (plugins/hpbandster/base.py:186).
+ * out_host[0]=loss, out_host[1]=accuracy.  synchronous.                                 */
+int bore_mlp_evaluate(bore_mlp *h, int model, const float *X_dev, const float *z_dev,
+                      int N, float l2, float *out_host, void *stream);
+
+/* ---- K3: batched bound-constrained L-BFGS-B -------------------------------------------
+ * Replaces the per-start scipy.optimize.minimize(fun, x0, method="L-BFGS-B", jac=True,
+ * bounds=..., options=dict(maxiter, ftol)) loop of bore/mixins.py:57-61 (also
+ * bore/optimizers/base.py:56-60), with K2 as the objective.  All S starts advance on
+ * device; the host only polls a counter.
+ *   X0_dev [S][D] fp64 start points (clipped into the box like SciPy does)
+ *   lo_host/hi_host [D] fp64 (+-inf allowed = unbounded side)
+ *   m (maxcor, <= BORE_LBFGSB_MAXCOR), ftol, gtol, maxiter, maxfun, maxls: SciPy options
+ *   work_dev: scratch of bore_lbfgsb_workspace_bytes(S, D, m) bytes
+ * Outputs (device): x_dev [S][D] fp64, fun_dev [S] fp64, nit/nfev/status/task_dev [S]
+ * int32 (task = SciPy's numeric task message code, e.g. 401/402/504; may be NULL).
+ * Returns after all starts terminated (synchronises `stream`).  *rounds_out (may be
+ * NULL) receives the number of lock-step evaluation rounds, *evals_out the total number
+ * of K2 point evaluations performed.                                                    */
+size_t bore_lbfgsb_workspace_bytes(int S, int D, int m);
+int bore_lbfgsb_minimize(bore_mlp *h, int model, int transform, const double *X0_dev,
+                         int S, const double *lo_host, const double *hi_host, int m,
+                         double ftol, double gtol, int maxiter, int maxfun, int maxls,
+                         void *work_dev, size_t work_bytes, double *x_dev,
+                         double *fun_dev, int32_t *nit_dev, int32_t *nfev_dev,
+                         int32_t *status_dev, int32_t *task_dev, int *rounds_out,
+                         long long *evals_out, void *stream);
+
+/* L-BFGS-B stepper alone, objective supplied by the caller (reverse communication):
+ * used to pin the on-device algorithm against SciPy's setulb request by request, and by
+ * minimize_multi_start() for objectives that are not a bore_mlp.
+ *   bore_lbfgsb_init: set up S states from X0; first requests are written to xreq_dev
+ *   bore_lbfgsb_step: consume f_dev[S] (fp32 or fp64 per `f_is_f64`), g_dev[S][D] for the
+ *     starts that were pending, advance each to its next request or to termination.
+ *     *pending_out = number of starts still asking for an evaluation (synchronises).
+ *   xreq_dev [S][D] fp64: current trial point of every start; pend_dev [S] int32 flags. */
+int bore_lbfgsb_init(const double *X0_dev, int S, int D, const double *lo_host,
+                     const double *hi_host, int m, double ftol, double gtol, int maxiter,
+                     int maxfun, int maxls, void *work_dev, size_t work_bytes,
+                     double *xreq_dev, int32_t *pend_dev, int device, void *stream);
+int bore_lbfgsb_step(const void *f_dev, const void *g_dev, int fg_is_f64, int S, int D,
+                     void *work_dev, double *xreq_dev, int32_t *pend_dev,
+                     int *pending_out, int device, void *stream);
+int bore_lbfgsb_results(int S, int D, void *work_dev, double *x_dev, double *fun_dev,
+                        int32_t *nit_dev, int32_t *nfev_dev, int32_t *status_dev,
+                        int32_t *task_dev, int device, void *stream);
+
+/* ---- K4: selection ---------------------------------------------------------------------
+ * bore_topk_smallest replaces np.argpartition(f_init, kth=num_starts-1)
+ * (bore/mixins.py:56): indices of the k smallest of f_dev[S] (ascending, ties by lower
+ * index) into idx_dev[k].
+ * bore_select_best replaces the final scan of bore/mixins.py:80-87: among starts with
+ * status in {0,1} and keep_dev[i]!=0 (keep_dev may be NULL), the FIRST minimum of fun.
+ * key_dev receives one int64: (orderable(-fun) << 31) | (0x7fffffff - (idx + idx_offset)),
+ * or 0 if no start qualifies -- ready for one NCCL max all-reduce across ranks.         */
+int bore_topk_smallest(const float *f_dev, int S, int k, int32_t *idx_dev, void *work_dev,
+                       size_t work_bytes, int device, void *stream);
+size_t bore_topk_workspace_bytes(int S, int k);
+int bore_select_best(const double *fun_dev, const int32_t *status_dev,
+                     const uint8_t *keep_dev, int S, int64_t idx_offset, int64_t *key_dev,
+                     int device, void *stream);
+
+/* ---- measurement helper -----------------------------------------------------------------
+ * FP32 FFMA-only microbenchmark (register-resident FMA chains, all SMs): the measured
+ * denominator for the FP32 roofline, since MEASURED_PEAKS.json carries only HBM and BF16.
+ * Returns TFLOP/s in *tflops_out; synchronous.                                          */
+int bore_bench_ffma_peak(int device, int iters, double *tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BORE_B200_H */
