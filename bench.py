@@ -1,0 +1,472 @@
+#!/usr/bin/env python
+"""bench.py -- the BORE-MLP hot path (fit -> multi-start argmax) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3]
+
+A "step" is one BO iteration on synthetic quantile-labelled data: fit the classifier (Keras
+semantics: `epochs` x ceil(N/64) Adam steps) then maximise it from S start points with the
+batched on-device L-BFGS-B.  Default workload = BASELINE.json configs[2], the configuration
+north_star's target is quoted on: synthetic 50-D Ackley, Dense64 x3 (+ sigmoid output), 2,000
+observations, 65,536 starts per GPU.  Multi-GPU is WEAK scaling: weights replicated (every rank
+runs the same deterministic fit), every rank optimises its own 65,536 starts, one NCCL max
+all-reduce on the packed (value, index) key picks the global argmax.
+
+`value` = value+input-gradient evaluations per second, whole job, inputs resident in HBM,
+timed with CUDA events (max over ranks).  `e2e` = the same through the public Python API
+(`model.fit` / `model.argmax`) with HOST numpy buffers, copies inside the timed region.
+`roofline` describes the kernel with the largest share of the step, `kernels` all of them.
+`cpu_baseline` (N=1 only) and `--impl reference` time the oracle's restatement of the reference's
+CPU path (NumPy Keras semantics + one scipy.optimize.minimize per start) -- TensorFlow cannot be
+installed in this image, see DESIGN.md -- on the box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[2]
+    "cfg3": dict(name="Ackley-50 / Dense64x3-ReLU+sigmoid / N=2000 / 65536 starts per GPU",
+                 dims=[50, 64, 64, 64, 1], acts=["relu", "relu", "relu", "sigmoid"],
+                 transform="identity", N=2000, epochs=31, batch=64, starts=65536, gamma=0.25,
+                 target="ackley"),
+    # BASELINE.json configs[1]
+    "cfg2": dict(name="Hartmann-6 / Dense32x2-ReLU+sigmoid / N=500 / 1024 starts",
+                 dims=[6, 32, 32, 1], acts=["relu", "relu", "sigmoid"], transform="identity",
+                 N=500, epochs=125, batch=64, starts=1024, gamma=0.25, target="hartmann6"),
+    # plugin defaults (BASELINE.json configs[4] network)
+    "cfg5": dict(name="8-D plugin net / Dense32x3-ELU logits + sigmoid transform / N=500 / 65536 starts",
+                 dims=[8, 32, 32, 32, 1], acts=["elu", "elu", "elu", "linear"], transform="sigmoid",
+                 N=500, epochs=125, batch=64, starts=65536, gamma=1 / 3, target="ackley"),
+}
+
+NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.4
+
+
+def ackley(X):
+    u = -32.768 + 65.536 * X
+    d = X.shape[1]
+    return (-20.0 * np.exp(-0.2 * np.sqrt(np.sum(u * u, axis=1) / d))
+            - np.exp(np.sum(np.cos(2 * np.pi * u), axis=1) / d) + 20.0 + np.e)
+
+
+_H_A = np.array([[10, 3, 17, 3.5, 1.7, 8], [0.05, 10, 17, 0.1, 8, 14], [3, 3.5, 1.7, 10, 17, 8],
+                 [17, 8, 0.05, 10, 0.1, 14]])
+_H_P = 1e-4 * np.array([[1312, 1696, 5569, 124, 8283, 5886], [2329, 4135, 8307, 3736, 1004, 9991],
+                        [2348, 1451, 3522, 2883, 3047, 6650], [4047, 8828, 8732, 5743, 1091, 381]])
+
+
+def hartmann6(X):
+    al = np.array([1.0, 1.2, 3.0, 3.2])
+    inner = np.einsum("ij,nij->ni", _H_A, (X[:, None, :] - _H_P[None]) ** 2)
+    return -np.sum(al * np.exp(-inner), axis=1)
+
+
+def make_problem(wl, seed):
+    rs = np.random.RandomState(seed)
+    D = wl["dims"][0]
+    X = rs.uniform(size=(wl["N"], D))
+    y = {"ackley": ackley, "hartmann6": hartmann6}[wl["target"]](X)
+    z = y < np.quantile(y, wl["gamma"])
+    perms = np.stack([rs.permutation(wl["N"]) for _ in range(wl["epochs"])]).astype(np.int32)
+    return X, z, perms
+
+
+def flops_per_eval(dims):
+    return 4 * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+
+
+def flops_per_fit_step(dims, batch):
+    W = sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+    P = W + sum(dims[1:])
+    return batch * (6 * W - 2 * dims[0] * dims[1]) + 12 * P
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu),
+                                          "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)),
+                    reasons=sorted(reasons), samples=len(sm), power_w_max=float(max(power)))
+
+
+# ------------------------------------------------------------------------------ reference arm
+def _ref_worker(args):
+    weights, acts, transform, X0 = args
+    from scipy.optimize import Bounds
+    from threadpoolctl import threadpool_limits
+    from oracle import argmax as am
+    n = X0.shape[1]
+    with threadpool_limits(1):  # batch-of-1 matmuls: BLAS threading only adds contention
+        r = am.minimize_starts(weights, acts, X0, Bounds(np.zeros(n), np.ones(n)), transform=transform)
+    return int(r["nfev"].sum()), float(r["fun"].min())
+
+
+def reference_step(wl, X, z, perms, w0, X0, pool, cores):
+    """One bounded-sample step of the restated reference CPU path.  Returns (fit_s, argmax_s,
+    evals in the sample)."""
+    from oracle import keras_mlp as km
+    from threadpoolctl import threadpool_limits
+    w = [a.copy() for a in w0]
+    t0 = time.perf_counter()
+    with threadpool_limits(1):
+        km.fit(w, wl["acts"], X, z, wl["epochs"], wl["batch"], perms)
+    t1 = time.perf_counter()
+    chunks = np.array_split(X0, cores)
+    jobs = [(w, wl["acts"], wl["transform"], c) for c in chunks if len(c)]
+    if pool is None:
+        outs = [_ref_worker(j) for j in jobs]
+    else:
+        outs = pool.map(_ref_worker, jobs)
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1, sum(o[0] for o in outs)
+
+
+def run_reference(args, wl, rank, world):
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from oracle import keras_mlp as km
+    cores = os.cpu_count() or 1
+    X, z, perms = make_problem(wl, seed=0)
+    w0 = km.init_weights(wl["dims"], 0)
+    S_ref = min(wl["starts"], 64 * cores)
+    X0 = np.random.RandomState(1).uniform(size=(S_ref, wl["dims"][0]))
+    pool = mp.get_context("fork").Pool(cores) if cores > 1 else None
+    for _ in range(args.warmup):
+        reference_step(wl, X, z, perms, w0, X0[:cores * 4], pool, cores)
+    tf = ta = 0.0
+    ev = 0
+    for _ in range(args.steps):
+        a, b, c = reference_step(wl, X, z, perms, w0, X0, pool, cores)
+        tf += a; ta += b; ev += c
+    if pool is not None:
+        pool.close()
+    K = args.steps
+    scale = wl["starts"] / S_ref
+    full_step_s = tf / K + (ta / K) * scale          # linear in the number of starts
+    evals_full = ev / K * scale
+    value = evals_full / full_step_s
+    line = {
+        "impl": "reference", "metric": "mlp_value_and_input_grad_evals_per_sec", "value": value,
+        "unit": "evals/s", "n_gpus": args.gpus, "steps": K, "warmup": args.warmup,
+        "ms_per_step": 1e3 * (tf + ta) / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 MLP / f64 L-BFGS-B", "data": "synthetic",
+        "config": {"workload": wl["name"], "starts_per_gpu": wl["starts"], "observations": wl["N"],
+                   "adam_steps": wl["epochs"] * (-(-wl["N"] // wl["batch"]))},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port",
+                         "sample": f"full fit ({wl['epochs']} epochs, serial) + {S_ref} of "
+                                   f"{wl['starts']} starts spread over {cores} processes per step; "
+                                   "value extrapolated linearly in the number of starts; NumPy "
+                                   "restatement of Keras + the installed SciPy L-BFGS-B, not TF"},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "bo_iterations_per_sec": 1.0 / full_step_s,
+        "phases": {"fit_ms": 1e3 * tf / K, "argmax_sample_ms": 1e3 * ta / K},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ our arm
+def run_ours(args, wl, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from bore_b200 import ops, _lib
+    from bore_b200.engine import ffma_peak_tflops
+    from bore_b200.layers import Dense
+    from bore_b200.models import MaximizableSequential
+    from bore_b200 import distributed as bd
+    from oracle import keras_mlp as km  # init weights only (Glorot with a seed) + cpu_baseline
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = _lib.require_cuda()
+    dims, acts, D, S = wl["dims"], wl["acts"], wl["dims"][0], wl["starts"]
+    X, z, perms = make_problem(wl, seed=0)              # the same problem on every rank
+    w0 = km.init_weights(dims, 0)
+    model = MaximizableSequential(transform=ops.TRANSFORMS[wl["transform"]], device=local_rank)
+    for i, (u, a) in enumerate(zip(dims[1:], acts)):
+        model.add(Dense(u, activation=a, input_dim=D if i == 0 else None))
+    model.compile(optimizer="adam", loss="binary_crossentropy" if acts[-1] == "sigmoid" else
+                  __import__("bore_b200").BinaryCrossentropy(from_logits=True))
+    model.set_weights(w0)
+    net = model._engine(D)
+    bounds = [(0.0, 1.0)] * D
+    lo, hi = np.zeros(D), np.ones(D)
+    tname = model._min_transform_name()
+
+    # ---- resident inputs (this rank's shard of the start points: its own seed) ----
+    Xd = net.to_device(X, np.float32)
+    zd = net.to_device(z.astype(np.float32), np.float32)
+    pd = net.to_device(perms, np.int32)
+    X0 = np.random.RandomState(1000 + rank).uniform(size=(S, D))
+    X0d = net.to_device(X0, np.float64)
+    X0f = X0d.to(torch.float32)
+    params = net.params_tensor()
+    w0d = params.clone()
+    loss_d = torch.empty(1, wl["epochs"], dtype=torch.float32, device=dev)
+    zbuf = torch.empty(S, dtype=torch.float32, device=dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    opts = dict(m=10, ftol=1e-9, gtol=1e-5, maxiter=1000, maxfun=15000, maxls=20)
+
+    def reset_state():
+        params.copy_(w0d)
+        net.reset_optimizer()
+
+    def step_resident(timers=None):
+        """fit -> screening predict -> batched L-BFGS-B -> first-minimum key (-> NCCL max)."""
+        reset_state()                                      # same work every step (see config)
+        if timers is not None:
+            ev[0].record()
+        net.fit_dev(Xd, zd, wl["N"], wl["batch"], wl["epochs"], pd, loss_dev=loss_d)
+        if timers is not None:
+            ev[1].record()
+        net.predict_dev(X0f, zbuf)                         # maxima's screening pass (mixins.py:50)
+        res = net.lbfgsb_dev(X0d, lo, hi, transform=tname, **opts)
+        key = net.select_best(res["fun"], res["status"], idx_offset=rank * S)
+        rec_fn = lambda i: torch.cat([res["x"][i], res["fun"][i:i + 1]])
+        gidx, rec = bd.global_winner(key, rec_fn, S * world, D + 1)
+        if timers is not None:
+            ev[2].record()
+            torch.cuda.synchronize()
+            timers["fit_ms"] += ev[0].elapsed_time(ev[1])
+            timers["argmax_ms"] += ev[1].elapsed_time(ev[2])
+        return res, gidx, rec
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    peak_ffma = ffma_peak_tflops(local_rank)
+    peaks = {}
+    mp_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(mp_path):
+        peaks = json.load(open(mp_path))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)"
+
+    import ctypes as C
+
+    # ---- warm-up ----
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    # ---- timed region: EXACTLY K steps, CUDA events, barrier + sync on both sides ----
+    lib.bore_lbfgsb_profile(1)
+    prof = np.zeros(5)
+    agg = dict(k2_ms=0.0, step_ms=0.0, rounds=0, bytes=0.0, evals=0.0)
+    timers = dict(fit_ms=0.0, argmax_ms=0.0)
+    sampler = ClockSampler(local_rank)
+    total_evals = 0
+    barrier()
+    sampler.start()
+    t_ev0, t_ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_ev0.record()
+    for _ in range(args.steps):
+        res, gidx, rec = step_resident(timers)
+        total_evals += res["evals"]
+        lib.bore_lbfgsb_last_profile(prof.ctypes.data_as(C.POINTER(C.c_double)))
+        agg["k2_ms"] += prof[0]; agg["step_ms"] += prof[1]; agg["rounds"] += int(prof[2])
+        agg["bytes"] += prof[3]; agg["evals"] += prof[4]
+    t_ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    lib.bore_lbfgsb_profile(0)
+    elapsed_ms = t_ev0.elapsed_time(t_ev1)
+    t = torch.tensor([elapsed_ms, float(total_evals)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        elapsed_ms, total_evals_all = tmax[0].item(), tsum[1].item()
+    else:
+        total_evals_all = float(total_evals)
+    K = args.steps
+    ms_per_step = elapsed_ms / K
+    value = total_evals_all / (elapsed_ms * 1e-3)
+
+    # ---- e2e: the public API with HOST buffers (H2D/D2H inside the timed region) ----
+    rs = np.random.RandomState(2000 + rank)
+    e2e_steps = max(2, min(K, 3))
+    reset_state()
+
+    def api_step():
+        model.fit(X, z, epochs=wl["epochs"], batch_size=wl["batch"], verbose=0, permutations=perms)
+        if world > 1:
+            return model.argmax_sharded(bounds, num_starts=S, random_state=rs)
+        return model.argmax(bounds, num_starts=S, num_samples=S, print_fn=None, random_state=rs)
+    api_step()  # warm
+    barrier()
+    t0 = time.perf_counter()
+    e2e_evals = 0
+    for _ in range(e2e_steps):
+        r = api_step()
+        e2e_evals += model._last_stats["evals"]
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s, float(e2e_evals)], dtype=torch.float64, device=dev)
+    if world > 1:
+        a = te.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
+        b = te.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        e2e_s, e2e_evals = a[0].item(), b[1].item()
+    h2d = X.size * 4 + z.size * 4 + perms.size * 4 + S * D * 8
+    d2h = wl["epochs"] * 4 + (D + 5) * 8 + 8
+
+    if rank != 0:
+        return
+    # ---- per-kernel accounting over the timed region (CUDA events on the launch stream) ----
+    F_eval = flops_per_eval(dims)
+    n_adam = wl["epochs"] * (-(-wl["N"] // wl["batch"]))
+    k2_tflops = agg["evals"] * F_eval / (agg["k2_ms"] * 1e-3) / 1e12
+    step_gbs = agg["bytes"] / (agg["step_ms"] * 1e-3) / 1e9
+    fit_tflops = K * n_adam * flops_per_fit_step(dims, wl["batch"]) / (timers["fit_ms"] * 1e-3) / 1e12
+    tot = timers["fit_ms"] + timers["argmax_ms"]
+    kernels = [
+        dict(name="lbfgsb_step_kernel (K3 stepper)", bound="hbm", ms_per_step=agg["step_ms"] / K,
+             share=agg["step_ms"] / tot, launches_per_step=agg["rounds"] / K, achieved=step_gbs,
+             peak=hbm_peak, unit="GB/s", frac=step_gbs / hbm_peak, peak_source=hbm_src),
+        dict(name="mlp_eval_kernel<grad> (K2 value+input-grad)", bound="fp32_ffma",
+             ms_per_step=agg["k2_ms"] / K, share=agg["k2_ms"] / tot,
+             launches_per_step=agg["rounds"] / K, achieved=k2_tflops, peak=peak_ffma,
+             unit="TFLOP/s", frac=k2_tflops / peak_ffma,
+             peak_source="FFMA microbenchmark measured in this run (nominal %.1f)" % NOMINAL_FP32_TFLOPS,
+             frac_of_nominal=k2_tflops / NOMINAL_FP32_TFLOPS),
+        dict(name="fit_kernel (K1 fused training, 1 model = 1 CTA)", bound="latency (1 SM)",
+             ms_per_step=timers["fit_ms"] / K, share=timers["fit_ms"] / tot, launches_per_step=1,
+             achieved=fit_tflops, peak=peak_ffma / 148, unit="TFLOP/s",
+             frac=fit_tflops / (peak_ffma / 148), peak_source="one SM's share of the FFMA peak"),
+    ]
+    dom = max(kernels[:2], key=lambda k: k["ms_per_step"])
+    traffic = None
+    ncu_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(ncu_path):
+        try:
+            traffic = json.load(open(ncu_path)).get(dom["name"].split(" ")[0])
+        except Exception:
+            traffic = None
+    roofline = dict(kernel=dom["name"], bound=dom["bound"] if dom["bound"] == "hbm" else "fp32_ffma",
+                    achieved=dom["achieved"], peak=dom["peak"], unit=dom["unit"], frac=dom["frac"],
+                    traffic=traffic, peak_source=dom["peak_source"],
+                    share_of_step=dom["share"], launches_per_step=dom["launches_per_step"])
+    line = {
+        "metric": "mlp_value_and_input_grad_evals_per_sec", "value": value, "unit": "evals/s",
+        "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 MLP / f64 L-BFGS-B", "data": "synthetic",
+        "config": {"workload": wl["name"], "starts_per_gpu": S, "observations": wl["N"],
+                   "adam_steps": n_adam, "parallelism": f"starts sharded x{world}, weights replicated",
+                   "l2_cache": "per-start L-BFGS-B state %.2f GB per GPU streams through HBM every "
+                               "round (>> 126 MB L2); no explicit flush" %
+                               (S * (256 + (4 * D + D * 21 + 300) * 8) / 1e9),
+                   "step": "weights and Adam state reset to the same seed before every step"},
+        "bo_iterations_per_sec": 1e3 / ms_per_step,
+        "phases": {"fit_ms": timers["fit_ms"] / K, "argmax_ms": timers["argmax_ms"] / K,
+                   "lbfgsb_rounds": agg["rounds"] / K, "evals_per_step_per_gpu": agg["evals"] / K,
+                   "argmax_evals_per_sec": world * agg["evals"] / (timers["argmax_ms"] * 1e-3)},
+        "roofline": roofline, "kernels": kernels,
+        "e2e": {"value": e2e_evals / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / e2e_steps,
+                "steps": e2e_steps, "api": "MaximizableSequential.fit + .argmax (numpy in/out)"},
+        "gpu_launches": int(K * 4 + 2 * agg["rounds"] + K * 2),
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(wl, X, z, perms, w0)
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(wl, X, z, perms, w0):
+    """The oracle port timed on ONE host core (the reference is single-process and serial),
+    bounded: the full fit + a sample of the starts."""
+    S_cpu = 1024 if wl["dims"][0] < 20 else 768
+    X0 = np.random.RandomState(1).uniform(size=(S_cpu, wl["dims"][0]))
+    tf, ta, ev = reference_step(wl, X, z, perms, w0, X0, None, 1)
+    scale = wl["starts"] / S_cpu
+    full = tf + ta * scale
+    return {"value": ev * scale / full, "unit": "evals/s", "cores": 1, "kind": "port",
+            "sample": f"1 process: full fit ({wl['epochs']} epochs, {tf:.2f} s) + {S_cpu} of "
+                      f"{wl['starts']} starts ({ta:.1f} s, {ev} evals), extrapolated linearly in "
+                      "starts; NumPy restatement of Keras + installed SciPy L-BFGS-B (not TF)",
+            "argmax_evals_per_sec": ev / ta, "adam_steps_per_sec":
+                wl["epochs"] * (-(-wl["N"] // wl["batch"])) / tf,
+            "host_cores_available": os.cpu_count()}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    from bore_b200 import distributed as bd
+    rank, local_rank, world = bd.env_world()
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+        return
+    if world > 1:
+        bd.init_process_group("nccl")
+    run_ours(args, wl, rank, local_rank, world)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -30,23 +30,28 @@ SIGNATURES = {
     "bore_mlp_get_weights": (C.c_int, [vp, C.c_int, vp]),
     "bore_mlp_set_adam_state": (C.c_int, [vp, C.c_int, vp, vp, C.c_int64]),
     "bore_mlp_get_adam_state": (C.c_int, [vp, C.c_int, vp, vp, C.POINTER(C.c_int64)]),
+    "bore_mlp_reset_optimizer": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+    "bore_mlp_set_optimizer": (C.c_int, [vp, C.c_float, C.c_float, C.c_float, C.c_float]),
     "bore_mlp_params_dev": (C.c_int, [vp, C.POINTER(vp)]),
     "bore_mlp_predict": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp]),
     "bore_mlp_value_and_grad": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp]),
     "bore_mlp_fit": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int,
-                               vp, C.c_int, C.c_float, vp, vp]),
-    "bore_mlp_evaluate": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, C.c_float, vp, vp]),
+                               vp, C.c_int, vp, vp]),
+    "bore_mlp_evaluate": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp, vp]),
+    "bore_mlp_set_regularizers": (C.c_int, [vp, vp, vp]),
     "bore_lbfgsb_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "bore_lbfgsb_minimize": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_int,
                                        C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
                                        vp, C.c_size_t, vp, vp, vp, vp, vp, vp,
                                        c_int_p, C.POINTER(C.c_longlong), vp]),
+    "bore_lbfgsb_profile": (C.c_int, [C.c_int]),
+    "bore_lbfgsb_last_profile": (C.c_int, [c_double_p]),
     "bore_lbfgsb_init": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_double, C.c_double,
                                    C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp, vp, C.c_int, vp]),
     "bore_lbfgsb_step": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, c_int_p,
                                    C.c_int, vp]),
     "bore_lbfgsb_results": (C.c_int, [C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp]),
-    "bore_topk_smallest": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_size_t, C.c_int, vp]),
+    "bore_topk_smallest": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_size_t, C.c_int, vp]),
     "bore_topk_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "bore_select_best": (C.c_int, [vp, vp, vp, C.c_int, C.c_int64, vp, C.c_int, vp]),
     "bore_bench_ffma_peak": (C.c_int, [C.c_int, C.c_int, c_double_p]),

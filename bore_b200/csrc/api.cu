@@ -61,6 +61,7 @@ int bore_mlp_create(int n_layers, const int *dims, const int *acts, int n_models
   }
   d.n_params = off;
   h->n_models = n_models;
+  h->lr = 1e-3f; h->beta1 = 0.9f; h->beta2 = 0.999f; h->eps = 1e-7f;  // Keras "adam"
   h->device = device;
   cudaDeviceProp prop;
   BORE_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -134,6 +135,38 @@ int bore_mlp_get_adam_state(bore_mlp *h, int model, float *m_host, float *v_host
   long long t = 0;
   BORE_CUDA(cudaMemcpy(&t, h->adam_t + model, sizeof(t), cudaMemcpyDeviceToHost));
   *iterations = t;
+  return 0;
+}
+
+int bore_mlp_reset_optimizer(bore_mlp *h, int model0, int count, void *stream) {
+  BORE_CHECK(h != nullptr, "NULL handle");
+  BORE_CHECK(model0 >= 0 && count >= 1 && model0 + count <= h->n_models,
+             "bore_mlp_reset_optimizer: models [%d,%d) outside [0,%d)", model0, model0 + count,
+             h->n_models);
+  BORE_CUDA(cudaSetDevice(h->device));
+  const size_t np = h->desc.n_params;
+  cudaStream_t st = (cudaStream_t)stream;
+  BORE_CUDA(cudaMemsetAsync(h->adam_m + model0 * np, 0, count * np * sizeof(float), st));
+  BORE_CUDA(cudaMemsetAsync(h->adam_v + model0 * np, 0, count * np * sizeof(float), st));
+  BORE_CUDA(cudaMemsetAsync(h->adam_t + model0, 0, count * sizeof(long long), st));
+  return 0;
+}
+
+int bore_mlp_set_optimizer(bore_mlp *h, float lr, float beta1, float beta2, float eps) {
+  BORE_CHECK(h != nullptr, "NULL handle");
+  BORE_CHECK(lr > 0.f && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f,
+             "bore_mlp_set_optimizer: invalid Adam hyper-parameters");
+  h->lr = lr; h->beta1 = beta1; h->beta2 = beta2; h->eps = eps;
+  return 0;
+}
+
+int bore_mlp_set_regularizers(bore_mlp *h, const float *l2_kernel_host, const float *l2_bias_host) {
+  BORE_CHECK(h != nullptr && l2_kernel_host && l2_bias_host, "NULL argument");
+  for (int l = 0; l < h->desc.n_layers; ++l) {
+    BORE_CHECK(l2_kernel_host[l] >= 0.f && l2_bias_host[l] >= 0.f, "negative l2 factor");
+    h->l2k[l] = l2_kernel_host[l];
+    h->l2b[l] = l2_bias_host[l];
+  }
   return 0;
 }
 

@@ -49,6 +49,8 @@ struct bore_mlp {
   float *adam_m;       // [n_models][n_params]
   float *adam_v;       // [n_models][n_params]
   long long *adam_t;   // [n_models]   Keras `iterations`
+  float lr, beta1, beta2, eps;  // Adam hyper-parameters
+  float l2k[BORE_MAX_LAYERS], l2b[BORE_MAX_LAYERS];  // l2 regularisers per layer
 };
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }

@@ -1,0 +1,478 @@
+// K1: fused classifier training (sm_100a, FP32 FFMA) -- the whole Keras `fit` in one launch.
+//
+// Replaces keras Model.fit(X, z, epochs, batch_size, shuffle=True) with optimizer="adam" and
+// binary cross-entropy (README.rst:66,93; bore/plugins/hpbandster/base.py:156-157,184), which
+// in the reference is epochs*ceil(N/B) TensorFlow dispatches of ~20 tiny ops each.
+//
+// One CTA per model; grid = number of models trained concurrently (seeds / BO problems /
+// per-budget classifiers).  Per minibatch step, entirely inside the CTA:
+//   gather   rows perm[e][s*B .. ) of X into shared memory, transposed to [feature][sample]
+//   forward  Dense layers as register-tiled (4 samples x 4 units per thread) FFMA GEMMs on
+//            shared-memory weights; activations kept for the reverse pass
+//   loss     sigmoid_cross_entropy_with_logits on the final pre-activation (both Keras forms,
+//            see oracle/keras_mlp.py:bce_with_logits), mean over the batch (+ l2 terms)
+//   reverse  delta_{l-1} = (delta_l W_l^T) . act'(h_{l-1}) on a transposed copy of the weights
+//   update   dW_l = h_{l-1}^T delta_l accumulated in registers by the thread that owns the
+//            weight, Adam applied in place (Keras form: eps outside the bias correction),
+//            both weight layouts rewritten; Adam slots m, v stream through L2.
+// Weights never leave shared memory during the run; HBM traffic is the minibatch gather
+// (B*(D+1)*4 bytes per step) plus the per-epoch loss.
+#include "common.cuh"
+
+namespace {
+
+constexpr int FIT_THREADS = 256;
+
+__device__ __forceinline__ float f_act(int a, float v) {
+  switch (a) {
+    case BORE_ACT_RELU: return fmaxf(v, 0.f);
+    case BORE_ACT_ELU: return v > 0.f ? v : expm1f(v);
+    case BORE_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    case BORE_ACT_TANH: return tanhf(v);
+    default: return v;
+  }
+}
+__device__ __forceinline__ float f_act_bwd(int a, float h) {
+  switch (a) {
+    case BORE_ACT_RELU: return h > 0.f ? 1.f : 0.f;
+    case BORE_ACT_ELU: return h > 0.f ? 1.f : h + 1.f;
+    case BORE_ACT_SIGMOID: return h * (1.f - h);
+    case BORE_ACT_TANH: return 1.f - h * h;
+    default: return 1.f;
+  }
+}
+__device__ __forceinline__ float stable_sigmoid(float u) {
+  if (u >= 0.f) return 1.f / (1.f + expf(-u));
+  const float e = expf(u);
+  return e / (1.f + e);
+}
+
+struct FitPlan {
+  int w[BORE_MAX_LAYERS];    // W_l  [in][JP]          (all Dense layers incl. final)
+  int wt[BORE_MAX_LAYERS];   // W_l^T [out][KP]        (layers 1.. only: layer 0 needs no reverse)
+  int b[BORE_MAX_LAYERS];    // bias [JP]
+  int h[BORE_MAX_LAYERS + 1];// activations [dim][BS]; h[0] = input batch
+  int dl[2];                 // delta ping/pong [maxw][BS]
+  int zb;                    // labels [BS]
+  int red;                   // reduction scratch [32]
+  int idx;                   // gathered row indices [BS] (ints)
+  int total;                 // floats
+  int BS;
+};
+
+__host__ __device__ inline int r4(int a) { return (a + 3) & ~3; }
+
+__host__ __device__ inline void make_fit_plan(const MlpDesc &d, int batch, FitPlan &p) {
+  const int L = d.n_layers;
+  int BS = r4(batch) + 4;
+  p.BS = BS;
+  int off = 0, maxw = 1;
+  for (int l = 0; l < L; ++l) {
+    const int in = d.dims[l], out = d.dims[l + 1];
+    p.w[l] = off; off += in * r4(out);
+    p.b[l] = off; off += r4(out);
+    p.wt[l] = off; if (l > 0) off += out * r4(in);
+    if (out > maxw) maxw = out;
+  }
+  for (int l = 0; l <= L; ++l) { p.h[l] = off; off += d.dims[l] * BS; }
+  p.dl[0] = off; off += maxw * BS;
+  p.dl[1] = off; off += maxw * BS;
+  p.zb = off; off += BS;
+  p.red = off; off += 32;
+  p.idx = off; off += BS;
+  p.total = r4(off);
+}
+
+struct FitArgs {
+  MlpDesc d;
+  FitPlan P;
+  float *params, *adam_m, *adam_v;
+  long long *adam_t;
+  int model0;
+  const float *X, *z;
+  int N, shared_data, batch, epochs;
+  const int *perm;
+  int shared_perm;
+  float l2k[BORE_MAX_LAYERS], l2b[BORE_MAX_LAYERS];
+  int any_l2;
+  float *loss_out;
+  float lr, beta1, beta2, eps;
+};
+
+__device__ __forceinline__ float block_sum(float v, float *red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  const int nw = blockDim.x >> 5;
+  for (int i = 0; i < nw; ++i) t += red[i];
+  return t;
+}
+
+__global__ void __launch_bounds__(FIT_THREADS) fit_kernel(const FitArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const MlpDesc &d = a.d;
+  const FitPlan &P = a.P;
+  const int L = d.n_layers, BS = P.BS;
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const int model = a.model0 + blockIdx.x;
+  float *gp = a.params + (size_t)model * d.n_params;
+  float *gm = a.adam_m + (size_t)model * d.n_params;
+  float *gv = a.adam_v + (size_t)model * d.n_params;
+  const float *X = a.X + (a.shared_data ? 0 : (size_t)blockIdx.x * a.N * d.dims[0]);
+  const float *zg = a.z + (a.shared_data ? 0 : (size_t)blockIdx.x * a.N);
+  const int *perm = a.perm + (a.shared_perm ? 0 : (size_t)blockIdx.x * a.epochs * a.N);
+  int *idxb = reinterpret_cast<int *>(sm + P.idx);
+  float *red = sm + P.red;
+  const int D = d.dims[0];
+
+  // ---- stage the weights: W_l [in][JP], W_l^T [out][KP] (l>0), bias ----
+  for (int l = 0; l < L; ++l) {
+    const int in = d.dims[l], out = d.dims[l + 1], JP = r4(out), KP = r4(in);
+    for (int e = tid; e < in * JP; e += NT) {
+      const int k = e / JP, j = e - k * JP;
+      sm[P.w[l] + e] = j < out ? gp[d.w_off[l] + k * out + j] : 0.f;
+    }
+    for (int e = tid; e < JP; e += NT) sm[P.b[l] + e] = e < out ? gp[d.b_off[l] + e] : 0.f;
+    if (l > 0)
+      for (int e = tid; e < out * KP; e += NT) {
+        const int j = e / KP, k = e - j * KP;
+        sm[P.wt[l] + e] = k < in ? gp[d.w_off[l] + k * out + j] : 0.f;
+      }
+  }
+  long long t_step = a.adam_t[model];
+  __syncthreads();
+
+  const int steps_per_epoch = (a.N + a.batch - 1) / a.batch;
+  for (int ep = 0; ep < a.epochs; ++ep) {
+    float epoch_tot = 0.f;
+    for (int st = 0; st < steps_per_epoch; ++st) {
+      const int s0 = st * a.batch;
+      const int nb = min(a.batch, a.N - s0);
+      const int BP = r4(nb);
+      // ---- gather the minibatch (transposed) ----
+      for (int p = tid; p < BP; p += NT) {
+        const int row = p < nb ? perm[(size_t)ep * a.N + s0 + p] : -1;
+        idxb[p] = row;
+        sm[P.zb + p] = row >= 0 ? zg[row] : 0.f;
+      }
+      __syncthreads();
+      for (int e = tid; e < BP * D; e += NT) {
+        const int p = e / D, k = e - p * D;
+        const int row = idxb[p];
+        sm[P.h[0] + k * BS + p] = row >= 0 ? X[(size_t)row * D + k] : 0.f;
+      }
+      __syncthreads();
+
+      // ---- forward ----
+      for (int l = 0; l < L; ++l) {
+        const int in = d.dims[l], out = d.dims[l + 1], JP = r4(out);
+        const float *A = sm + P.h[l];
+        const float *W = sm + P.w[l];
+        const float *bs = sm + P.b[l];
+        float *H = sm + P.h[l + 1];
+        const int act = (l == L - 1) ? BORE_ACT_LINEAR : d.act[l];  // loss works on the logit
+        const int tpn = BP / 4, ntile = tpn * (JP / 4);
+        for (int tt = tid; tt < ntile; tt += NT) {
+          const int tp = tt % tpn, tj = tt / tpn;
+          float acc[4][4] = {};
+          const float *ap = A + tp * 4;
+          const float *wp = W + tj * 4;
+#pragma unroll 4
+          for (int k = 0; k < in; ++k) {
+            const float4 av = *reinterpret_cast<const float4 *>(ap + k * BS);
+            const float4 wv = *reinterpret_cast<const float4 *>(wp + k * JP);
+            const float a4[4] = {av.x, av.y, av.z, av.w};
+            const float w4[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int u = 0; u < 4; ++u) acc[i][u] = fmaf(a4[i], w4[u], acc[i][u]);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = tj * 4 + u;
+            if (j < out) {
+              const float b = bs[j];
+              float4 o;
+              o.x = f_act(act, acc[0][u] + b);
+              o.y = f_act(act, acc[1][u] + b);
+              o.z = f_act(act, acc[2][u] + b);
+              o.w = f_act(act, acc[3][u] + b);
+              *reinterpret_cast<float4 *>(H + j * BS + tp * 4) = o;
+            }
+          }
+        }
+        __syncthreads();
+      }
+
+      // ---- loss and dL/dlogit (mean over the batch) ----
+      const float inv_nb = 1.f / (float)nb;
+      float lsum = 0.f;
+      {
+        const float *U = sm + P.h[L];  // [1][BS] logits
+        float *dz = sm + P.dl[0];
+        for (int p = tid; p < BP; p += NT) {
+          float dl = 0.f;
+          if (p < nb) {
+            const float u = U[p], zz = sm[P.zb + p];
+            lsum += fmaxf(u, 0.f) - u * zz + log1pf(expf(-fabsf(u)));
+            dl = (stable_sigmoid(u) - zz) * inv_nb;
+          }
+          dz[p] = dl;
+        }
+      }
+      float loss = block_sum(lsum, red) * inv_nb;  // (also the barrier publishing dz)
+
+      // ---- Adam scalars for this step (Keras: t starts at 1) ----
+      t_step += 1;
+      const float b1p = powf(a.beta1, (float)t_step), b2p = powf(a.beta2, (float)t_step);
+      const float alpha = a.lr * sqrtf(1.f - b2p) / (1.f - b1p);
+      const float om1 = 1.f - a.beta1, om2 = 1.f - a.beta2;
+      float reg = 0.f;
+
+      // ---- reverse + update, top layer first ----
+      int cur = 0;
+      for (int l = L - 1; l >= 0; --l) {
+        const int in = d.dims[l], out = d.dims[l + 1], JP = r4(out), KP = r4(in);
+        const float *DL = sm + P.dl[cur];  // delta_l [out][BS]
+        // (1) delta_{l-1} = (delta_l W_l^T) . act'(h_{l-1}) into the other buffer
+        if (l > 0) {
+          const float *WT = sm + P.wt[l];
+          const float *Hin = sm + P.h[l];
+          float *DN = sm + P.dl[cur ^ 1];
+          const int actp = d.act[l - 1];
+          const int tpn = BP / 4, ntile = tpn * (KP / 4);
+          for (int tt = tid; tt < ntile; tt += NT) {
+            const int tp = tt % tpn, tk = tt / tpn;
+            float acc[4][4] = {};
+            const float *ap = DL + tp * 4;
+            const float *wp = WT + tk * 4;
+#pragma unroll 4
+            for (int j = 0; j < out; ++j) {
+              const float4 av = *reinterpret_cast<const float4 *>(ap + j * BS);
+              const float4 wv = *reinterpret_cast<const float4 *>(wp + j * KP);
+              const float a4[4] = {av.x, av.y, av.z, av.w};
+              const float w4[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) acc[i][u] = fmaf(a4[i], w4[u], acc[i][u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int k = tk * 4 + u;
+              if (k < in) {
+                const float4 hv = *reinterpret_cast<const float4 *>(Hin + k * BS + tp * 4);
+                float4 o;
+                o.x = acc[0][u] * f_act_bwd(actp, hv.x);
+                o.y = acc[1][u] * f_act_bwd(actp, hv.y);
+                o.z = acc[2][u] * f_act_bwd(actp, hv.z);
+                o.w = acc[3][u] * f_act_bwd(actp, hv.w);
+                *reinterpret_cast<float4 *>(DN + k * BS + tp * 4) = o;
+              }
+            }
+          }
+        }
+        __syncthreads();  // delta_{l-1} done with W_l before W_l changes
+        // (2) dW_l = h_{l-1}^T delta_l (+2*l2*w), Adam in place; thread tile 4(k) x 4(j),
+        //     k strided so that consecutive lanes read consecutive activation rows
+        {
+          const float *Hin = sm + P.h[l];
+          float *W = sm + P.w[l];
+          float *WT = sm + P.wt[l];
+          const float l2k = a.l2k[l], l2b = a.l2b[l];
+          const int tkn = (in + 3) / 4, tjn = JP / 4;
+          const int ntile = tkn * tjn;
+          for (int tt = tid; tt < ntile; tt += NT) {
+            const int tk = tt % tkn, tj = tt / tkn;
+            float acc[4][4] = {};
+            int kk[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) kk[u] = min(tk + u * tkn, in - 1);
+            for (int p = 0; p < BP; p += 4) {
+              float4 hv[4], dv[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                hv[u] = *reinterpret_cast<const float4 *>(Hin + kk[u] * BS + p);
+                dv[u] = *reinterpret_cast<const float4 *>(DL + min(tj * 4 + u, out - 1) * BS + p);
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  acc[i][u] = fmaf(hv[i].x, dv[u].x, acc[i][u]);
+                  acc[i][u] = fmaf(hv[i].y, dv[u].y, acc[i][u]);
+                  acc[i][u] = fmaf(hv[i].z, dv[u].z, acc[i][u]);
+                  acc[i][u] = fmaf(hv[i].w, dv[u].w, acc[i][u]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int k = tk + i * tkn;
+              if (k >= in) continue;
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int j = tj * 4 + u;
+                if (j >= out) continue;
+                const int gi = d.w_off[l] + k * out + j;
+                float wv = W[k * JP + j];
+                float g = acc[i][u];
+                if (l2k != 0.f) { reg += l2k * wv * wv; g += 2.f * l2k * wv; }
+                float m = gm[gi], v = gv[gi];
+                m += (g - m) * om1;
+                v += (g * g - v) * om2;
+                wv -= (m * alpha) / (sqrtf(v) + a.eps);
+                gm[gi] = m; gv[gi] = v;
+                W[k * JP + j] = wv;
+                if (l > 0) WT[j * KP + k] = wv;
+              }
+            }
+          }
+          // bias: db_j = sum_p delta_l[j][p]
+          for (int j = tid; j < out; j += NT) {
+            float g = 0.f;
+            for (int p = 0; p < BP; ++p) g += DL[j * BS + p];
+            const int gi = d.b_off[l] + j;
+            float bv = sm[P.b[l] + j];
+            if (l2b != 0.f) { reg += l2b * bv * bv; g += 2.f * l2b * bv; }
+            float m = gm[gi], v = gv[gi];
+            m += (g - m) * om1;
+            v += (g * g - v) * om2;
+            bv -= (m * alpha) / (sqrtf(v) + a.eps);
+            gm[gi] = m; gv[gi] = v;
+            sm[P.b[l] + j] = bv;
+          }
+        }
+        __syncthreads();
+        cur ^= 1;
+      }
+      if (a.any_l2) loss += block_sum(reg, red);
+      epoch_tot += loss * (float)nb;
+    }
+    if (tid == 0 && a.loss_out) a.loss_out[(size_t)blockIdx.x * a.epochs + ep] = epoch_tot / (float)a.N;
+  }
+
+  // ---- write the trained weights back ----
+  __syncthreads();
+  for (int l = 0; l < L; ++l) {
+    const int in = d.dims[l], out = d.dims[l + 1], JP = r4(out);
+    for (int e = tid; e < in * out; e += NT) {
+      const int k = e / out, j = e - k * out;
+      gp[d.w_off[l] + e] = sm[P.w[l] + k * JP + j];
+    }
+    for (int e = tid; e < out; e += NT) gp[d.b_off[l] + e] = sm[P.b[l] + e];
+  }
+  if (tid == 0) a.adam_t[model] = t_step;
+}
+
+// ---------------------------------------------------------------- evaluate (loss, accuracy)
+__global__ void __launch_bounds__(256)
+evaluate_kernel(const MlpDesc d, const float *__restrict__ params, const float *__restrict__ logits,
+                const float *__restrict__ z, int N, const float *__restrict__ l2vec, float *out2) {
+  // logits: final pre-activation computed by K0 on a copy of the model with a linear head
+  __shared__ float red[32];
+  float ls = 0.f, acc = 0.f, reg = 0.f;
+  const int act_last = d.act[d.n_layers - 1];
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const float u = logits[i], zz = z[i];
+    ls += fmaxf(u, 0.f) - u * zz + log1pf(expf(-fabsf(u)));
+    const float outv = act_last == BORE_ACT_SIGMOID ? stable_sigmoid(u) : u;
+    acc += ((outv > 0.5f ? 1.f : 0.f) == zz) ? 1.f : 0.f;  // Keras quirk: thresholds the OUTPUT
+  }
+  if (l2vec)  // l2vec[2l] = kernel factor, l2vec[2l+1] = bias factor of layer l
+    for (int l = 0; l < d.n_layers; ++l) {
+      const int nk = d.dims[l] * d.dims[l + 1], nbias = d.dims[l + 1];
+      for (int i = threadIdx.x; i < nk; i += blockDim.x) { const float w = params[d.w_off[l] + i]; reg += l2vec[2 * l] * w * w; }
+      for (int i = threadIdx.x; i < nbias; i += blockDim.x) { const float w = params[d.b_off[l] + i]; reg += l2vec[2 * l + 1] * w * w; }
+    }
+  ls = block_sum(ls, red);
+  acc = block_sum(acc, red);
+  reg = block_sum(reg, red);
+  if (threadIdx.x == 0) {
+    out2[0] = ls / (float)N + reg;
+    out2[1] = acc / (float)N;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int bore_mlp_fit(bore_mlp *h, int model0, int count, const float *X_dev, const float *z_dev, int N,
+                 int shared_data, int batch_size, int epochs, const int32_t *perm_dev,
+                 int shared_perm, float *loss_out_dev, void *stream) {
+  BORE_CHECK(h != nullptr, "NULL handle");
+  BORE_CHECK(model0 >= 0 && count >= 1 && model0 + count <= h->n_models,
+             "bore_mlp_fit: models [%d,%d) outside [0,%d)", model0, model0 + count, h->n_models);
+  BORE_CHECK(N >= 1 && batch_size >= 1 && epochs >= 0, "bore_mlp_fit: N=%d batch=%d epochs=%d", N,
+             batch_size, epochs);
+  BORE_CHECK(X_dev && z_dev && perm_dev, "bore_mlp_fit: NULL buffer");
+  const int last = h->desc.act[h->desc.n_layers - 1];
+  BORE_CHECK(last == BORE_ACT_SIGMOID || last == BORE_ACT_LINEAR,
+             "bore_mlp_fit: binary cross-entropy needs a sigmoid or linear (from_logits) output layer");
+  BORE_CUDA(cudaSetDevice(h->device));
+  if (epochs == 0) return 0;
+  FitArgs a;
+  a.d = h->desc;
+  const int B = batch_size < N ? batch_size : N;
+  make_fit_plan(a.d, B, a.P);
+  const size_t smem = (size_t)a.P.total * sizeof(float);
+  BORE_CHECK(smem <= 227 * 1024, "bore_mlp_fit: model + batch of %d need %zu B of shared memory", B, smem);
+  a.params = h->params; a.adam_m = h->adam_m; a.adam_v = h->adam_v; a.adam_t = h->adam_t;
+  a.model0 = model0;
+  a.X = X_dev; a.z = z_dev; a.N = N; a.shared_data = shared_data; a.batch = batch_size;
+  a.epochs = epochs; a.perm = perm_dev; a.shared_perm = shared_perm;
+  a.any_l2 = 0;
+  for (int l = 0; l < BORE_MAX_LAYERS; ++l) {
+    a.l2k[l] = l < a.d.n_layers ? h->l2k[l] : 0.f;
+    a.l2b[l] = l < a.d.n_layers ? h->l2b[l] : 0.f;
+    if (a.l2k[l] != 0.f || a.l2b[l] != 0.f) a.any_l2 = 1;
+  }
+  a.loss_out = loss_out_dev;
+  a.lr = h->lr; a.beta1 = h->beta1; a.beta2 = h->beta2; a.eps = h->eps;
+  BORE_CUDA(cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fit_kernel<<<count, FIT_THREADS, smem, (cudaStream_t)stream>>>(a);
+  BORE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bore_mlp_evaluate(bore_mlp *h, int model, const float *X_dev, const float *z_dev, int N,
+                      float *out_host, void *stream_) {
+  BORE_CHECK(h != nullptr, "NULL handle");
+  BORE_CHECK(model >= 0 && model < h->n_models, "model index %d outside [0,%d)", model, h->n_models);
+  BORE_CHECK(N >= 1 && X_dev && z_dev && out_host, "bore_mlp_evaluate: bad arguments");
+  BORE_CUDA(cudaSetDevice(h->device));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  float *logits = nullptr, *out2 = nullptr;
+  BORE_CUDA(cudaMalloc(&logits, (size_t)N * sizeof(float)));
+  BORE_CUDA(cudaMalloc(&out2, (2 + 2 * BORE_MAX_LAYERS) * sizeof(float)));
+  float l2host[2 * BORE_MAX_LAYERS];
+  bool any = false;
+  for (int l = 0; l < BORE_MAX_LAYERS; ++l) {
+    l2host[2 * l] = l < h->desc.n_layers ? h->l2k[l] : 0.f;
+    l2host[2 * l + 1] = l < h->desc.n_layers ? h->l2b[l] : 0.f;
+    any = any || l2host[2 * l] != 0.f || l2host[2 * l + 1] != 0.f;
+  }
+  float *l2dev = out2 + 2;
+  cudaMemcpyAsync(l2dev, l2host, sizeof(l2host), cudaMemcpyHostToDevice, stream);
+  // forward with a linear head = the logits the loss is defined on
+  bore_mlp tmp = *h;
+  tmp.desc.act[tmp.desc.n_layers - 1] = BORE_ACT_LINEAR;
+  int rc = launch_mlp_eval(&tmp, model, false, BORE_TRANSFORM_IDENTITY, 0, X_dev, N, logits, nullptr,
+                           nullptr, nullptr, stream);
+  if (!rc) {
+    evaluate_kernel<<<1, 256, 0, stream>>>(h->desc, h->params + (size_t)model * h->desc.n_params,
+                                           logits, z_dev, N, any ? l2dev : nullptr, out2);
+    cudaMemcpyAsync(out_host, out2, 2 * sizeof(float), cudaMemcpyDeviceToHost, stream);
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { bore_set_error("bore_mlp_evaluate: %s", cudaGetErrorString(e)); rc = -2; }
+  }
+  cudaFree(logits);
+  cudaFree(out2);
+  return rc;
+}
+
+}  // extern "C"

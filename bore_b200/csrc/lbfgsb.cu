@@ -1,0 +1,579 @@
+// K3: batched bound-constrained L-BFGS-B on device (sm_100a).
+//
+// Replaces the serial per-start scipy.optimize.minimize loop of bore/mixins.py:57-61.
+// Structure: lock-step reverse communication, entirely on the device --
+//
+//     round r:   K2 (mlp_eval.cu) evaluates f,g for every start still asking for it, read
+//                through a compacted active list;
+//                lbfgsb_step_kernel: one WARP per active start consumes f,g and runs the
+//                L-BFGS-B state machine of lbfgsb_core.h (Cauchy point, subspace
+//                minimisation, More'-Thuente line search, BFGS update) until the start
+//                either terminates or posts its next trial point, appending itself to the
+//                next round's active list.
+//
+// Finished starts drop out of the list, so late rounds cost only as much as the few starts
+// that are still running (the per-start evaluation counts vary by >10x).
+// The host only polls the active counter, pipelined one chunk of rounds behind the launches.
+//
+// State.  Per start, a contiguous block in HBM: scalars | xold gold d z | W=[Y S] (n x (2m+1))
+// | SY SS WT.  A step loads only what it touches: a step that just continues a line search
+// reads the scalars and 4 vectors; the matrices are streamed into shared memory only when a
+// new iteration starts, and written back only after a BFGS update.
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+#include "lbfgsb_core.h"
+
+namespace {
+
+constexpr int SCAL_BYTES = 256;
+static_assert(sizeof(LbScal) <= SCAL_BYTES, "LbScal grew past its slot");
+
+struct LbLayout {
+  // offsets in bytes from the workspace base
+  size_t lo, hi, nbd, cnt, evals, lists, xf, f, g, pend, blocks, block_stride, xreq, total;
+};
+
+__host__ __device__ inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+inline LbLayout make_layout(int S, int n, int m, bool own_xreq) {
+  LbLayout L;
+  size_t o = 0;
+  L.lo = o; o += align_up(n * sizeof(double), 16);
+  L.hi = o; o += align_up(n * sizeof(double), 16);
+  L.nbd = o; o += align_up(n * sizeof(int), 16);
+  L.cnt = o; o += 16;      // 3 rotating active counters (+pad)
+  L.evals = o; o += 16;    // unsigned long long evals, bytes
+  L.lists = o; o += align_up((size_t)2 * S * sizeof(int), 16);
+  L.xf = o; o += align_up((size_t)S * n * sizeof(float), 16);
+  L.f = o; o += align_up((size_t)S * sizeof(float), 16);
+  L.g = o; o += align_up((size_t)S * n * sizeof(float), 16);
+  L.pend = o; o += align_up((size_t)S * sizeof(int), 16);
+  L.block_stride = align_up(SCAL_BYTES + ((size_t)4 * n + (size_t)n * LB_LDW(m) + 3 * m * m) *
+                                             sizeof(double), 16);
+  L.blocks = o; o += L.block_stride * S;
+  L.xreq = o; if (own_xreq) o += align_up((size_t)S * n * sizeof(double), 16);
+  L.total = o;
+  return L;
+}
+
+struct LbDev {
+  LbParams P;
+  int S;
+  char *blocks;
+  size_t block_stride;
+  double *xreq;   // [S][n] last requested point (final x once a start is done)
+  float *xf;      // [S][n] fp32 copy of the request for the MLP kernel (may be NULL)
+  const void *F;  // [S]    objective values, indexed by start
+  const void *G;  // [S][n] gradients
+  int *lists;     // [2][S]
+  int *cnt;       // [3]
+  unsigned long long *evals;
+  unsigned long long *bytes;  // algorithmic bytes moved by the stepper
+  int *pend;      // [S] (may be NULL)
+};
+
+// lazy loader of the limited-memory matrices (global block -> the warp's smem workspace)
+struct BlockMem {
+  const LbParams &P;
+  LbWork &w;
+  LbScal &s;
+  double *gW, *gM;  // global W and [sy ss wt]
+  bool loaded = false, is_dirty = false, vec_dirty = false;
+  __host__ __device__ BlockMem(const LbParams &P_, LbWork &w_, LbScal &s_, double *gW_, double *gM_)
+      : P(P_), w(w_), s(s_), gW(gW_), gM(gM_) {}
+  __host__ __device__ void load() {
+    if (loaded) return;
+    loaded = true;
+    if (s.col == 0) return;  // empty memory: nothing valid to read
+    const int nW = P.n * LB_LDW(P.m), nM = 3 * P.m * P.m;
+    for (int i = LB_LANE; i < nW; i += 32) w.W[i] = gW[i];
+    for (int i = LB_LANE; i < nM; i += 32) w.sy[i] = gM[i];  // sy, ss, wt are contiguous
+    LB_SYNC();
+  }
+  __host__ __device__ void dirty() { is_dirty = true; }
+  __host__ __device__ void dirty_vec() { vec_dirty = true; }
+  __host__ __device__ void store() {
+    if (!is_dirty) return;
+    const int nW = P.n * LB_LDW(P.m), nM = 3 * P.m * P.m;
+    LB_SYNC();
+    for (int i = LB_LANE; i < nW; i += 32) gW[i] = w.W[i];
+    for (int i = LB_LANE; i < nM; i += 32) gM[i] = w.sy[i];
+  }
+};
+
+__device__ __forceinline__ int init_iwhere(const LbParams &P, int i) {
+  const int nb = P.nbd[i];
+  if (nb == 0) return -1;
+  return (nb == 2 && P.hi[i] - P.lo[i] <= 0.0) ? 3 : 0;
+}
+
+// ---------------------------------------------------------------- init: one warp per start
+__global__ void __launch_bounds__(128) lbfgsb_init_kernel(LbDev D, const double *__restrict__ X0) {
+  const int n = D.P.n;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    D.cnt[0] = D.S; D.cnt[1] = 0; D.cnt[2] = 0;
+    *D.evals = 0ULL;
+    *D.bytes = 0ULL;
+  }
+  for (int sid = warp; sid < D.S; sid += nwarps) {
+    for (int i = lane; i < n; i += 32) {
+      double xi = X0[(size_t)sid * n + i];
+      const int nb = D.P.nbd[i];
+      if (nb > 0) {  // SciPy clips x0 into the box (_lbfgsb_py.py:359); `active` does the same
+        if (nb <= 2 && xi <= D.P.lo[i]) xi = D.P.lo[i];
+        else if (nb >= 2 && xi >= D.P.hi[i]) xi = D.P.hi[i];
+      }
+      D.xreq[(size_t)sid * n + i] = xi;
+      if (D.xf) D.xf[(size_t)sid * n + i] = (float)xi;
+    }
+    if (lane == 0) {
+      LbScal s;
+      s.f = 0; s.fold = 0; s.theta = 1.0; s.gd = 0; s.gdold = 0; s.dtd = 0; s.dnorm = 0;
+      s.stp = 0; s.stpmx = 0; s.sbgnrm = 0;
+      s.finit = s.ginit = s.gtest = s.gx = s.gy = s.fx = s.fy = 0;
+      s.stx = s.sty = s.stmin = s.stmax = s.width = s.width1 = 0;
+      s.phase = LB_PH_START; s.col = 0; s.iupdat = 0; s.iter = 0; s.nit = 0;
+      s.nfev = 1;  // the evaluation at x0
+      s.ifun = 0; s.iback = 0; s.updatd = 0; s.status = -1; s.task = 0;
+      s.brackt = 0; s.stage = 0; s.ls_task = LB_LS_START; s.nskip = 0; s.nintol = 0;
+      *reinterpret_cast<LbScal *>(D.blocks + D.block_stride * sid) = s;
+      D.lists[sid] = sid;
+      if (D.pend) D.pend[sid] = 1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- one lock-step round
+template <typename FG>
+__global__ void __launch_bounds__(128)
+lbfgsb_step_kernel(LbDev D, int round, size_t warp_bytes) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = D.P.n, m = D.P.m;
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int cur = round % 3, nxt = (round + 1) % 3, clr = (round + 2) % 3;
+  if (blockIdx.x == 0 && threadIdx.x == 0) D.cnt[clr] = 0;
+  const int n_active = D.cnt[cur];
+  const int *list_cur = D.lists + (size_t)(round & 1) * D.S;
+  int *list_nxt = D.lists + (size_t)((round + 1) & 1) * D.S;
+
+  unsigned char *base = smem_raw + warp_bytes * wib;
+  LbWork w;
+  lb_carve(w, reinterpret_cast<double *>(base),
+           reinterpret_cast<int *>(base + lb_work_doubles(n, m) * sizeof(double)), n, m);
+  const FG *F = static_cast<const FG *>(D.F);
+  const FG *G = static_cast<const FG *>(D.G);
+
+  for (int idx = blockIdx.x * wpb + wib; idx < n_active; idx += gridDim.x * wpb) {
+    const int sid = list_cur[idx];
+    char *blk = D.blocks + D.block_stride * sid;
+    LbScal s = *reinterpret_cast<const LbScal *>(blk);
+    double *gvec = reinterpret_cast<double *>(blk + SCAL_BYTES);
+    double *gW = gvec + 4 * n;
+    double *gM = gW + (size_t)n * LB_LDW(m);
+    double *xr = D.xreq + (size_t)sid * n;
+
+    s.f = (double)F[sid];
+    for (int i = lane; i < n; i += 32) {
+      w.x[i] = xr[i];
+      w.g[i] = (double)G[(size_t)sid * n + i];
+      w.iwhere[i] = init_iwhere(D.P, i);
+    }
+    if (s.phase == LB_PH_LNSRCH) {
+      for (int i = lane; i < n; i += 32) {
+        w.t[i] = gvec[i];
+        w.r[i] = gvec[n + i];
+        w.d[i] = gvec[2 * n + i];
+        w.z[i] = gvec[3 * n + i];
+      }
+    }
+    __syncwarp();
+    BlockMem mem(D.P, w, s, gW, gM);
+    const int col_in = s.col;
+    const bool was_ls = s.phase == LB_PH_LNSRCH;
+    const int pend = lb_advance(D.P, w, s, mem);
+    __syncwarp();
+    if (lane == 0) {
+      // algorithmic traffic of this step: scalars r+w, f, g, x read; the 4 vectors if a line
+      // search was in flight; the valid part of the memory if a new iteration started; then
+      // what changed: request (fp64 + fp32 copy), the 4 vectors, the new (s,y) pair with its
+      // SY row / SS column and the refactored WT
+      unsigned long long b = 2 * sizeof(LbScal) + sizeof(FG) * (1 + n) + 8ull * n;
+      if (was_ls) b += 32ull * n;
+      if (mem.loaded && col_in > 0) b += 16ull * n * col_in + 24ull * col_in * col_in;
+      if (pend) b += 12ull * n; else b += 8ull * n;
+      if (pend && mem.vec_dirty) b += 32ull * n;
+      if (mem.is_dirty) b += 16ull * n + 16ull * s.col + 8ull * s.col * s.col;
+      atomicAdd(D.bytes, b);
+    }
+    if (pend) {
+      int changed = 0;
+      for (int i = lane; i < n; i += 32) {
+        const double xi = w.x[i];
+        changed |= (xr[i] != xi);
+        xr[i] = xi;
+        if (D.xf) D.xf[(size_t)sid * n + i] = (float)xi;
+      }
+      if (__any_sync(0xffffffffu, changed)) s.nfev += 1;
+      if (mem.vec_dirty) {
+        for (int i = lane; i < n; i += 32) {
+          gvec[i] = w.t[i];
+          gvec[n + i] = w.r[i];
+          gvec[2 * n + i] = w.d[i];
+          gvec[3 * n + i] = w.z[i];
+        }
+      }
+      mem.store();
+      if (lane == 0) {
+        const int pos = atomicAdd(&D.cnt[nxt], 1);
+        list_nxt[pos] = sid;
+        atomicAdd(D.evals, 1ULL);
+      }
+    } else {
+      for (int i = lane; i < n; i += 32) xr[i] = w.x[i];  // final iterate
+    }
+    if (lane == 0) {
+      *reinterpret_cast<LbScal *>(blk) = s;
+      if (D.pend) D.pend[sid] = pend;
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void lbfgsb_results_kernel(LbDev D, double *x, double *fun, int *nit, int *nfev,
+                                      int *status, int *task) {
+  const int n = D.P.n;
+  for (int sid = blockIdx.x * blockDim.x + threadIdx.x; sid < D.S; sid += gridDim.x * blockDim.x) {
+    const LbScal *s = reinterpret_cast<const LbScal *>(D.blocks + D.block_stride * sid);
+    if (fun) fun[sid] = s->f;
+    if (nit) nit[sid] = s->nit;
+    if (nfev) nfev[sid] = s->nfev;
+    if (status) status[sid] = s->status;
+    if (task) task[sid] = s->task;
+    if (x && x != D.xreq)
+      for (int i = 0; i < n; ++i) x[(size_t)sid * n + i] = D.xreq[(size_t)sid * n + i];
+  }
+}
+
+// ---------------------------------------------------------------- host side
+// optional per-kernel timing of bore_lbfgsb_minimize (CUDA events on the launch stream)
+struct LbProfile {
+  bool enabled = false;
+  std::vector<cudaEvent_t> pool;
+  double k2_ms = 0, step_ms = 0, bytes = 0, evals = 0;
+  int rounds = 0, k2_launches = 0, step_launches = 0;
+  cudaEvent_t get(size_t i) {
+    while (pool.size() <= i) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    return pool[i];
+  }
+};
+LbProfile g_prof;
+
+struct StepLaunch {
+  int grid, block;
+  size_t warp_bytes, smem;
+};
+
+int plan_step(int S, int n, int m, int sm_count, StepLaunch &L) {
+  L.warp_bytes = align_up(lb_work_doubles(n, m) * sizeof(double) + lb_work_ints(n) * sizeof(int), 16);
+  const size_t max_smem = 227 * 1024;
+  BORE_CHECK(L.warp_bytes <= max_smem, "lbfgsb: n=%d needs %zu B of shared memory per start", n,
+             L.warp_bytes);
+  int wpb = 4;
+  while (wpb > 1 && wpb * L.warp_bytes > max_smem) --wpb;
+  // prefer several small CTAs per SM over one large one
+  while (wpb > 1 && (max_smem / (wpb * L.warp_bytes + 1024)) < 2 &&
+         (max_smem / ((wpb - 1) * L.warp_bytes + 1024)) * (wpb - 1) >=
+             (max_smem / (wpb * L.warp_bytes + 1024)) * wpb)
+    --wpb;
+  L.block = wpb * 32;
+  L.smem = wpb * L.warp_bytes;
+  int per_sm = (int)(max_smem / (L.smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm * wpb > 32) per_sm = 32 / wpb;
+  L.grid = sm_count * per_sm;
+  const int need = (S + wpb - 1) / wpb;
+  if (L.grid > need) L.grid = need;
+  if (L.grid < 1) L.grid = 1;
+  return 0;
+}
+
+int setup_params(LbDev &D, const LbLayout &L, char *work, int S, int n, int m, const double *lo_h,
+                 const double *hi_h, double ftol, double gtol, int maxiter, int maxfun, int maxls,
+                 cudaStream_t stream) {
+  std::vector<double> lo(n), hi(n);
+  std::vector<int> nbd(n);
+  int cnstnd = 0, boxed = 1;
+  for (int i = 0; i < n; ++i) {
+    const bool Lb = !isinf(lo_h[i]), Ub = !isinf(hi_h[i]);
+    BORE_CHECK(!(Lb && Ub && lo_h[i] > hi_h[i]),
+               "LBFGSB - one of the lower bounds is greater than an upper bound.");
+    nbd[i] = Lb ? (Ub ? 2 : 1) : (Ub ? 3 : 0);
+    lo[i] = Lb ? lo_h[i] : 0.0;
+    hi[i] = Ub ? hi_h[i] : 0.0;
+    if (nbd[i] != 2) boxed = 0;
+    if (nbd[i] != 0) cnstnd = 1;
+  }
+  BORE_CUDA(cudaMemcpyAsync(work + L.lo, lo.data(), n * sizeof(double), cudaMemcpyHostToDevice, stream));
+  BORE_CUDA(cudaMemcpyAsync(work + L.hi, hi.data(), n * sizeof(double), cudaMemcpyHostToDevice, stream));
+  BORE_CUDA(cudaMemcpyAsync(work + L.nbd, nbd.data(), n * sizeof(int), cudaMemcpyHostToDevice, stream));
+  BORE_CUDA(cudaStreamSynchronize(stream));  // the host vectors die at return
+  D.P.n = n; D.P.m = m; D.P.maxiter = maxiter; D.P.maxfun = maxfun; D.P.maxls = maxls;
+  D.P.cnstnd = cnstnd; D.P.boxed = boxed; D.P.ftol = ftol; D.P.pgtol = gtol;
+  D.P.lo = reinterpret_cast<const double *>(work + L.lo);
+  D.P.hi = reinterpret_cast<const double *>(work + L.hi);
+  D.P.nbd = reinterpret_cast<const int *>(work + L.nbd);
+  D.S = S;
+  D.blocks = work + L.blocks;
+  D.block_stride = L.block_stride;
+  D.lists = reinterpret_cast<int *>(work + L.lists);
+  D.cnt = reinterpret_cast<int *>(work + L.cnt);
+  D.evals = reinterpret_cast<unsigned long long *>(work + L.evals);
+  D.bytes = D.evals + 1;
+  return 0;
+}
+
+// header kept at the very start of the external-API workspace so step/results can find things
+struct ExtHeader {
+  LbDev D;
+  int round;
+  int sm_count;
+};
+constexpr size_t EXT_HDR = 512;
+static_assert(sizeof(ExtHeader) <= EXT_HDR, "ExtHeader too large");
+
+int check_opts(int S, int D, int m, int maxls) {
+  BORE_CHECK(S >= 1, "lbfgsb: S=%d", S);
+  BORE_CHECK(D >= 1 && D <= BORE_MAX_DIM, "lbfgsb: D=%d outside [1,%d]", D, BORE_MAX_DIM);
+  BORE_CHECK(m >= 1 && m <= BORE_LBFGSB_MAXCOR, "lbfgsb: maxcor=%d outside [1,%d]", m,
+             BORE_LBFGSB_MAXCOR);
+  BORE_CHECK(maxls > 0, "maxls must be positive.");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t bore_lbfgsb_workspace_bytes(int S, int D, int m) {
+  if (S < 1 || D < 1 || m < 1) return 0;
+  return EXT_HDR + make_layout(S, D, m, false).total;
+}
+
+int bore_lbfgsb_minimize(bore_mlp *h, int model, int transform, const double *X0_dev, int S,
+                         const double *lo_host, const double *hi_host, int m, double ftol,
+                         double gtol, int maxiter, int maxfun, int maxls, void *work_dev,
+                         size_t work_bytes, double *x_dev, double *fun_dev, int32_t *nit_dev,
+                         int32_t *nfev_dev, int32_t *status_dev, int32_t *task_dev, int *rounds_out,
+                         long long *evals_out, void *stream_) {
+  BORE_CHECK(h != nullptr, "NULL handle");
+  BORE_CHECK(model >= 0 && model < h->n_models, "model index %d outside [0,%d)", model, h->n_models);
+  const int n = h->desc.dims[0];
+  if (check_opts(S, n, m, maxls)) return -1;
+  BORE_CHECK(transform >= 0 && transform <= BORE_TRANSFORM_EXP, "unknown transform code %d", transform);
+  BORE_CHECK(x_dev && X0_dev && work_dev, "NULL buffer");
+  BORE_CUDA(cudaSetDevice(h->device));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const LbLayout L = make_layout(S, n, m, false);
+  BORE_CHECK(work_bytes >= EXT_HDR + L.total, "lbfgsb workspace too small: %zu < %zu", work_bytes,
+             EXT_HDR + L.total);
+  char *work = static_cast<char *>(work_dev) + EXT_HDR;
+  LbDev D;
+  if (setup_params(D, L, work, S, n, m, lo_host, hi_host, ftol, gtol, maxiter, maxfun, maxls, stream))
+    return -1;
+  D.xreq = x_dev;
+  D.xf = reinterpret_cast<float *>(work + L.xf);
+  float *F = reinterpret_cast<float *>(work + L.f);
+  float *G = reinterpret_cast<float *>(work + L.g);
+  D.F = F; D.G = G;
+  D.pend = nullptr;
+  StepLaunch SL;
+  if (plan_step(S, n, m, h->sm_count, SL)) return -1;
+  BORE_CUDA(cudaFuncSetAttribute(lbfgsb_step_kernel<float>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL.smem));
+  {
+    const int blocks = std::min((S + 3) / 4, h->sm_count * 8);
+    lbfgsb_init_kernel<<<blocks, 128, 0, stream>>>(D, X0_dev);
+    BORE_CUDA(cudaGetLastError());
+  }
+  // pipelined polling: the active counter of chunk c is read while chunk c+1 is in flight
+  const int CHUNK = 4;
+  int *cnt_host = nullptr;
+  BORE_CUDA(cudaMallocHost(&cnt_host, 2 * sizeof(int)));
+  cudaEvent_t ev[2];
+  BORE_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+  BORE_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  int round = 0, rc = 0;
+  bool have_prev = false;
+  int slot = 0;
+  const long long max_rounds = (long long)maxfun + (long long)maxls + 8;
+  for (;;) {
+    for (int k = 0; k < CHUNK; ++k, ++round) {
+      const int *list = D.lists + (size_t)(round & 1) * S;
+      if (g_prof.enabled) cudaEventRecord(g_prof.get(3 * (size_t)round), stream);
+      rc = launch_mlp_eval(h, model, true, transform, 1, D.xf, S, F, G, list, D.cnt + round % 3, stream);
+      if (rc) break;
+      if (g_prof.enabled) cudaEventRecord(g_prof.get(3 * (size_t)round + 1), stream);
+      lbfgsb_step_kernel<float><<<SL.grid, SL.block, SL.smem, stream>>>(D, round, SL.warp_bytes);
+      if (g_prof.enabled) cudaEventRecord(g_prof.get(3 * (size_t)round + 2), stream);
+    }
+    if (rc) break;
+    if (cudaGetLastError() != cudaSuccess) { bore_set_error("lbfgsb_step_kernel launch failed"); rc = -2; break; }
+    cudaMemcpyAsync(&cnt_host[slot], D.cnt + round % 3, sizeof(int), cudaMemcpyDeviceToHost, stream);
+    cudaEventRecord(ev[slot], stream);
+    if (have_prev) {
+      cudaError_t e = cudaEventSynchronize(ev[slot ^ 1]);
+      if (e != cudaSuccess) { bore_set_error("lbfgsb: %s", cudaGetErrorString(e)); rc = -2; break; }
+      if (cnt_host[slot ^ 1] == 0) break;
+    }
+    have_prev = true;
+    slot ^= 1;
+    if (round > max_rounds) { bore_set_error("lbfgsb: exceeded %lld rounds", max_rounds); rc = -3; break; }
+  }
+  if (!rc) {
+    lbfgsb_results_kernel<<<std::min((S + 127) / 128, 1024), 128, 0, stream>>>(
+        D, x_dev, fun_dev, nit_dev, nfev_dev, status_dev, task_dev);
+    unsigned long long evals = 0;
+    cudaMemcpyAsync(&evals, D.evals, sizeof(evals), cudaMemcpyDeviceToHost, stream);
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { bore_set_error("lbfgsb: %s", cudaGetErrorString(e)); rc = -2; }
+    // `evals` counts the requests posted after x0; add the S initial evaluations
+    if (evals_out) *evals_out = (long long)evals + S;
+    if (rounds_out) *rounds_out = round;
+    if (g_prof.enabled && !rc) {
+      unsigned long long bytes = 0;
+      cudaMemcpy(&bytes, D.bytes, sizeof(bytes), cudaMemcpyDeviceToHost);
+      g_prof.k2_ms = g_prof.step_ms = 0;
+      for (int r = 0; r < round; ++r) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, g_prof.get(3 * (size_t)r), g_prof.get(3 * (size_t)r + 1));
+        cudaEventElapsedTime(&b, g_prof.get(3 * (size_t)r + 1), g_prof.get(3 * (size_t)r + 2));
+        g_prof.k2_ms += a;
+        g_prof.step_ms += b;
+      }
+      g_prof.rounds = round;
+      g_prof.k2_launches = g_prof.step_launches = round;
+      g_prof.bytes = (double)bytes;
+      g_prof.evals = (double)evals + S;
+    }
+  } else {
+    cudaStreamSynchronize(stream);
+  }
+  cudaEventDestroy(ev[0]);
+  cudaEventDestroy(ev[1]);
+  cudaFreeHost(cnt_host);
+  return rc;
+}
+
+// per-kernel timing of the NEXT bore_lbfgsb_minimize calls (bench.py's roofline leg)
+int bore_lbfgsb_profile(int enable) {
+  g_prof.enabled = enable != 0;
+  return 0;
+}
+// out[0] K2 total ms, out[1] stepper total ms, out[2] rounds (= launches of each kernel),
+// out[3] stepper algorithmic bytes, out[4] K2 point evaluations -- of the last profiled call
+int bore_lbfgsb_last_profile(double *out) {
+  BORE_CHECK(out != nullptr, "NULL argument");
+  out[0] = g_prof.k2_ms; out[1] = g_prof.step_ms; out[2] = g_prof.rounds;
+  out[3] = g_prof.bytes; out[4] = g_prof.evals;
+  return 0;
+}
+
+// ---------------------------------------------------------------- reverse-communication API
+int bore_lbfgsb_init(const double *X0_dev, int S, int n, const double *lo_host,
+                     const double *hi_host, int m, double ftol, double gtol, int maxiter,
+                     int maxfun, int maxls, void *work_dev, size_t work_bytes, double *xreq_dev,
+                     int32_t *pend_dev, int device, void *stream_) {
+  if (check_opts(S, n, m, maxls)) return -1;
+  BORE_CHECK(X0_dev && work_dev && xreq_dev && pend_dev, "NULL buffer");
+  BORE_CHECK(bore_device_count() > 0, "no CUDA device visible -- bore_b200 has no CPU fallback");
+  BORE_CUDA(cudaSetDevice(device));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const LbLayout L = make_layout(S, n, m, false);
+  BORE_CHECK(work_bytes >= EXT_HDR + L.total, "lbfgsb workspace too small: %zu < %zu", work_bytes,
+             EXT_HDR + L.total);
+  char *work = static_cast<char *>(work_dev) + EXT_HDR;
+  ExtHeader H;
+  memset(&H, 0, sizeof(H));
+  if (setup_params(H.D, L, work, S, n, m, lo_host, hi_host, ftol, gtol, maxiter, maxfun, maxls, stream))
+    return -1;
+  H.D.xreq = xreq_dev;
+  H.D.xf = nullptr;
+  H.D.F = nullptr; H.D.G = nullptr;
+  H.D.pend = pend_dev;
+  H.round = 0;
+  cudaDeviceProp prop;
+  BORE_CUDA(cudaGetDeviceProperties(&prop, device));
+  H.sm_count = prop.multiProcessorCount;
+  const int blocks = std::min((S + 3) / 4, H.sm_count * 8);
+  lbfgsb_init_kernel<<<blocks, 128, 0, stream>>>(H.D, X0_dev);
+  BORE_CUDA(cudaGetLastError());
+  BORE_CUDA(cudaMemcpyAsync(work_dev, &H, sizeof(H), cudaMemcpyHostToDevice, stream));
+  BORE_CUDA(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+int bore_lbfgsb_step(const void *f_dev, const void *g_dev, int fg_is_f64, int S, int n,
+                     void *work_dev, double *xreq_dev, int32_t *pend_dev, int *pending_out,
+                     int device, void *stream_) {
+  BORE_CHECK(f_dev && g_dev && work_dev, "NULL buffer");
+  BORE_CUDA(cudaSetDevice(device));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ExtHeader H;
+  BORE_CUDA(cudaMemcpyAsync(&H, work_dev, sizeof(H), cudaMemcpyDeviceToHost, stream));
+  BORE_CUDA(cudaStreamSynchronize(stream));
+  BORE_CHECK(H.D.S == S && H.D.P.n == n, "lbfgsb_step: workspace was initialised for S=%d D=%d",
+             H.D.S, H.D.P.n);
+  H.D.F = f_dev; H.D.G = g_dev;
+  H.D.xreq = xreq_dev; H.D.pend = pend_dev;
+  StepLaunch SL;
+  if (plan_step(S, n, H.D.P.m, H.sm_count, SL)) return -1;
+  if (fg_is_f64) {
+    BORE_CUDA(cudaFuncSetAttribute(lbfgsb_step_kernel<double>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL.smem));
+    lbfgsb_step_kernel<double><<<SL.grid, SL.block, SL.smem, stream>>>(H.D, H.round, SL.warp_bytes);
+  } else {
+    BORE_CUDA(cudaFuncSetAttribute(lbfgsb_step_kernel<float>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL.smem));
+    lbfgsb_step_kernel<float><<<SL.grid, SL.block, SL.smem, stream>>>(H.D, H.round, SL.warp_bytes);
+  }
+  BORE_CUDA(cudaGetLastError());
+  H.round += 1;
+  int pending = 0;
+  BORE_CUDA(cudaMemcpyAsync(&pending, H.D.cnt + H.round % 3, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  BORE_CUDA(cudaMemcpyAsync(work_dev, &H, sizeof(H), cudaMemcpyHostToDevice, stream));
+  BORE_CUDA(cudaStreamSynchronize(stream));
+  if (pending_out) *pending_out = pending;
+  return 0;
+}
+
+int bore_lbfgsb_results(int S, int n, void *work_dev, double *x_dev, double *fun_dev,
+                        int32_t *nit_dev, int32_t *nfev_dev, int32_t *status_dev, int32_t *task_dev,
+                        int device, void *stream_) {
+  BORE_CHECK(work_dev, "NULL buffer");
+  BORE_CUDA(cudaSetDevice(device));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ExtHeader H;
+  BORE_CUDA(cudaMemcpyAsync(&H, work_dev, sizeof(H), cudaMemcpyDeviceToHost, stream));
+  BORE_CUDA(cudaStreamSynchronize(stream));
+  BORE_CHECK(H.D.S == S && H.D.P.n == n, "lbfgsb_results: workspace was initialised for S=%d D=%d",
+             H.D.S, H.D.P.n);
+  lbfgsb_results_kernel<<<std::min((S + 127) / 128, 1024), 128, 0, stream>>>(
+      H.D, x_dev, fun_dev, nit_dev, nfev_dev, status_dev, task_dev);
+  BORE_CUDA(cudaGetLastError());
+  BORE_CUDA(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+}  // extern "C"

@@ -852,7 +852,17 @@ LB_HD void lb_finish(LbScal &s, int status, int task) {
   s.task = task;
 }
 
-LB_HD int lb_advance(const LbParams &P, LbWork &w, LbScal &s) {
+// `Mem` supplies the limited-memory matrices lazily: mem.load() is called once, right before
+// they are first needed (a step that only continues a line search never touches them), and
+// mem.dirty() when they were modified.
+struct LbNoMem {
+  LB_HD void load() {}
+  LB_HD void dirty() {}
+  LB_HD void dirty_vec() {}
+};
+
+template <class Mem>
+LB_HD int lb_advance(const LbParams &P, LbWork &w, LbScal &s, Mem &mem) {
   const int n = P.n, m = P.m;
   enum { ST_TESTS, ST_ITER, ST_REQUEST, ST_FAIL };
   int st;
@@ -885,6 +895,7 @@ LB_HD int lb_advance(const LbParams &P, LbWork &w, LbScal &s) {
   }
 
   for (;;) {
+    if (st == ST_TESTS || st == ST_ITER) mem.load();
     if (st == ST_TESTS) {
       // ---- termination tests (mainlb label 777) ----
       if (s.sbgnrm <= P.pgtol) { lb_finish(s, 0, 401); return 0; }
@@ -909,6 +920,7 @@ LB_HD int lb_advance(const LbParams &P, LbWork &w, LbScal &s) {
       } else {
         s.updatd = 1;
         s.iupdat += 1;
+        mem.dirty();
         lb_matupd(P, w, s, rr, dr);
         if (lb_formt(w.wt, w.sy, w.ss, m, s.col, s.theta)) lb_reset_memory(s);
       }
@@ -917,6 +929,7 @@ LB_HD int lb_advance(const LbParams &P, LbWork &w, LbScal &s) {
 
     if (st == ST_ITER) {
       // ---- new iteration (label 222): search direction ----
+      mem.dirty_vec();
       int nfree = n;
       for (;;) {
         if (!P.cnstnd && s.col > 0) {

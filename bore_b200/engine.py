@@ -1,0 +1,314 @@
+"""Host-side owner of one native model handle (``bore_mlp*``) and its device buffers.
+
+Everything numeric happens in libbore_b200.so (hand-written sm_100a kernels) through the C ABI
+of include/bore_b200.h; this class only moves buffers.  PyTorch is used for exactly three things:
+device memory (``torch.empty(..., device="cuda")``), pinned host staging buffers and the current
+CUDA stream.  There is no CPU fallback -- construction fails without a CUDA device.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+ACT_CODES = {"linear": 0, None: 0, "relu": 1, "elu": 2, "sigmoid": 3, "tanh": 4}
+TRANSFORM_CODES = {"identity": 0, "sigmoid": 1, "exp": 2}
+
+# scipy.optimize L-BFGS-B task codes -> message (scipy/optimize/_lbfgsb_py.py:49-90)
+_STATUS_MSG = {0: "CONVERGENCE", 1: "STOP", 2: "ABNORMAL"}
+_TASK_MSG = {0: "", 401: "NORM OF PROJECTED GRADIENT <= PGTOL",
+             402: "RELATIVE REDUCTION OF F <= FACTR*EPSMCH",
+             502: "TOTAL NO. OF F,G EVALUATIONS EXCEEDS LIMIT",
+             504: "TOTAL NO. OF ITERATIONS REACHED LIMIT"}
+
+
+def lbfgsb_message(status, task):
+    return _STATUS_MSG.get(int(status), "?") + ": " + _TASK_MSG.get(int(task), "")
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class NativeMLP:
+    """M independent MLPs of one architecture living on one GPU."""
+
+    def __init__(self, dims, acts, n_models=1, device=None):
+        self.lib = _lib.require_cuda()
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise _lib.BoreNativeError("torch sees no CUDA device; bore_b200 has no CPU fallback")
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.dims = [int(d) for d in dims]
+        self.acts = [a if a is not None else "linear" for a in acts]
+        assert len(self.acts) == len(self.dims) - 1
+        codes = [ACT_CODES[a] for a in self.acts]
+        self.n_models = int(n_models)
+        h = C.c_void_p()
+        dims_c = (C.c_int * len(self.dims))(*self.dims)
+        acts_c = (C.c_int * len(codes))(*codes)
+        _lib.check(self.lib.bore_mlp_create(len(codes), dims_c, acts_c, self.n_models, self.device,
+                                            C.byref(h)))
+        self.h = h
+        self.n_params = self.lib.bore_mlp_num_params(h)
+        self.D = self.dims[0]
+        self._work = None  # cached L-BFGS-B workspace (torch uint8 tensor)
+
+    def __del__(self):
+        h, self.h = getattr(self, "h", None), None
+        if h:
+            try:
+                self.lib.bore_mlp_destroy(h)
+            except Exception:
+                pass
+
+    # ------------------------------------------------------------------ helpers
+    def _tdev(self):
+        return _torch().device("cuda", self.device)
+
+    def _stream(self):
+        return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    def shapes(self):
+        out = []
+        for fi, fo in zip(self.dims[:-1], self.dims[1:]):
+            out += [(fi, fo), (fo,)]
+        return out
+
+    def _flatten(self, weights):
+        shp = self.shapes()
+        assert len(weights) == len(shp), f"expected {len(shp)} arrays, got {len(weights)}"
+        parts = []
+        for w, s in zip(weights, shp):
+            w = np.asarray(w, np.float32)
+            assert w.shape == s, f"weight shape {w.shape} != {s}"
+            parts.append(w.ravel())
+        return np.ascontiguousarray(np.concatenate(parts))
+
+    def _unflatten(self, flat):
+        out, o = [], 0
+        for s in self.shapes():
+            k = int(np.prod(s))
+            out.append(flat[o:o + k].reshape(s).copy())
+            o += k
+        return out
+
+    def to_device(self, a, dtype):
+        """numpy -> device tensor through a pinned staging buffer."""
+        torch = _torch()
+        a = np.ascontiguousarray(a, dtype=dtype)
+        t = torch.from_numpy(a)
+        try:
+            t = t.pin_memory()
+        except RuntimeError:
+            pass
+        return t.to(self._tdev(), non_blocking=True)
+
+    # ------------------------------------------------------------------ parameters
+    def set_weights(self, weights, model=0):
+        flat = self._flatten(weights)
+        _lib.check(self.lib.bore_mlp_set_weights(self.h, model, _np_ptr(flat)))
+
+    def get_weights(self, model=0):
+        flat = np.empty(self.n_params, np.float32)
+        _lib.check(self.lib.bore_mlp_get_weights(self.h, model, _np_ptr(flat)))
+        return self._unflatten(flat)
+
+    def set_adam_state(self, m, v, iterations, model=0):
+        mf, vf = self._flatten(m), self._flatten(v)
+        _lib.check(self.lib.bore_mlp_set_adam_state(self.h, model, _np_ptr(mf), _np_ptr(vf),
+                                                    int(iterations)))
+
+    def get_adam_state(self, model=0):
+        mf = np.empty(self.n_params, np.float32)
+        vf = np.empty(self.n_params, np.float32)
+        it = C.c_int64()
+        _lib.check(self.lib.bore_mlp_get_adam_state(self.h, model, _np_ptr(mf), _np_ptr(vf),
+                                                    C.byref(it)))
+        return self._unflatten(mf), self._unflatten(vf), it.value
+
+    def reset_optimizer(self, model0=0, count=None):
+        """Zero Adam's m, v, iterations on the current stream (asynchronous)."""
+        count = self.n_models - model0 if count is None else count
+        _lib.check(self.lib.bore_mlp_reset_optimizer(self.h, model0, count, self._stream()))
+
+    def set_optimizer(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7):
+        _lib.check(self.lib.bore_mlp_set_optimizer(self.h, lr, beta1, beta2, eps))
+
+    def set_regularizers(self, l2):
+        """``l2``: one factor for every kernel and bias, or a per-array sequence in Keras weight
+        order [k0, b0, k1, b1, ...]."""
+        L = len(self.acts)
+        v = [float(l2)] * (2 * L) if np.isscalar(l2) else [float(t) for t in l2]
+        assert len(v) == 2 * L
+        lk = np.ascontiguousarray(v[0::2], np.float32)
+        lb = np.ascontiguousarray(v[1::2], np.float32)
+        _lib.check(self.lib.bore_mlp_set_regularizers(self.h, _np_ptr(lk), _np_ptr(lb)))
+
+    def params_tensor(self):
+        """The flat [n_models, n_params] parameter block as a torch view (for NCCL broadcast)."""
+        torch = _torch()
+        p = C.c_void_p()
+        _lib.check(self.lib.bore_mlp_params_dev(self.h, C.byref(p)))
+        n = self.n_models * self.n_params
+
+        class _Holder:  # __cuda_array_interface__ view of native memory
+            pass
+        hd = _Holder()
+        hd.__cuda_array_interface__ = dict(shape=(n,), typestr="<f4", data=(p.value, False),
+                                           version=3)
+        return torch.as_tensor(hd, device=self._tdev()).view(self.n_models, self.n_params)
+
+    # ------------------------------------------------------------------ K0 / K2
+    def predict_dev(self, X_dev, out_dev=None, model=0):
+        torch = _torch()
+        S = X_dev.shape[0]
+        assert X_dev.dtype == torch.float32 and X_dev.is_contiguous() and X_dev.shape[1] == self.D
+        if out_dev is None:
+            out_dev = torch.empty(S, dtype=torch.float32, device=self._tdev())
+        _lib.check(self.lib.bore_mlp_predict(self.h, model, _ptr(X_dev), S, _ptr(out_dev),
+                                             self._stream()))
+        return out_dev
+
+    def predict(self, X, model=0):
+        """Keras ``predict`` (bore/mixins.py:50): X (S, D) -> (S, 1) float32."""
+        X = np.asarray(X)
+        if X.shape[0] == 0:
+            return np.zeros((0, 1), np.float32)
+        out = self.predict_dev(self.to_device(X, np.float32), model=model)
+        return out.cpu().numpy().reshape(-1, 1)
+
+    def value_and_grad_dev(self, X_dev, transform="identity", negate=True, f_dev=None, g_dev=None,
+                           model=0):
+        torch = _torch()
+        S = X_dev.shape[0]
+        assert X_dev.dtype == torch.float32 and X_dev.is_contiguous() and X_dev.shape[1] == self.D
+        if f_dev is None:
+            f_dev = torch.empty(S, dtype=torch.float32, device=self._tdev())
+        if g_dev is None:
+            g_dev = torch.empty(S, self.D, dtype=torch.float32, device=self._tdev())
+        _lib.check(self.lib.bore_mlp_value_and_grad(self.h, model, TRANSFORM_CODES[transform],
+                                                    1 if negate else 0, _ptr(X_dev), S,
+                                                    _ptr(f_dev), _ptr(g_dev), self._stream()))
+        return f_dev, g_dev
+
+    def value_and_grad(self, X, transform="identity", negate=True, model=0):
+        """f = T(+-u(x)), g = df/dx for every row of X (float32 results)."""
+        X = np.atleast_2d(np.asarray(X))
+        f, g = self.value_and_grad_dev(self.to_device(X, np.float32), transform, negate,
+                                       model=model)
+        return f.cpu().numpy(), g.cpu().numpy()
+
+    # ------------------------------------------------------------------ K3
+    def _workspace(self, nbytes):
+        torch = _torch()
+        if self._work is None or self._work.numel() < nbytes:
+            self._work = torch.empty(int(nbytes), dtype=torch.uint8, device=self._tdev())
+        return self._work
+
+    def lbfgsb_dev(self, X0_dev, lo, hi, transform="identity", m=10, ftol=1e-9, gtol=1e-5,
+                   maxiter=1000, maxfun=15000, maxls=20, model=0):
+        """All rows of X0_dev (S, D) float64 minimised on device.  Returns a dict of device
+        tensors (x, fun, nit, nfev, status, task) plus ints rounds / evals."""
+        torch = _torch()
+        S, D = X0_dev.shape
+        assert D == self.D and X0_dev.dtype == torch.float64 and X0_dev.is_contiguous()
+        lo = np.ascontiguousarray(np.broadcast_to(np.asarray(lo, np.float64), (D,)))
+        hi = np.ascontiguousarray(np.broadcast_to(np.asarray(hi, np.float64), (D,)))
+        nbytes = self.lib.bore_lbfgsb_workspace_bytes(S, D, m)
+        work = self._workspace(nbytes)
+        dev = self._tdev()
+        x = torch.empty(S, D, dtype=torch.float64, device=dev)
+        fun = torch.empty(S, dtype=torch.float64, device=dev)
+        ints = torch.empty(4, S, dtype=torch.int32, device=dev)
+        rounds, evals = C.c_int(), C.c_longlong()
+        _lib.check(self.lib.bore_lbfgsb_minimize(
+            self.h, model, TRANSFORM_CODES[transform], _ptr(X0_dev), S, _np_ptr(lo), _np_ptr(hi),
+            int(m), float(ftol), float(gtol), int(maxiter), int(maxfun), int(maxls),
+            _ptr(work), work.numel(), _ptr(x), _ptr(fun), _ptr(ints[0]), _ptr(ints[1]),
+            _ptr(ints[2]), _ptr(ints[3]), C.byref(rounds), C.byref(evals), self._stream()))
+        return dict(x=x, fun=fun, nit=ints[0], nfev=ints[1], status=ints[2], task=ints[3],
+                    rounds=rounds.value, evals=evals.value)
+
+    def lbfgsb(self, X0, lo, hi, **kw):
+        X0 = np.atleast_2d(np.asarray(X0, np.float64))
+        r = self.lbfgsb_dev(self.to_device(X0, np.float64), lo, hi, **kw)
+        return {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in r.items()}
+
+    # ------------------------------------------------------------------ K4
+    def topk_smallest(self, f_dev, k, negate=False):
+        """Indices (int32, device) of the k smallest entries of f_dev (or of -f_dev), ascending,
+        ties by lower index -- np.argpartition's job at bore/mixins.py:56."""
+        torch = _torch()
+        S = f_dev.shape[0]
+        assert f_dev.dtype == torch.float32 and f_dev.is_contiguous()
+        idx = torch.empty(int(k), dtype=torch.int32, device=self._tdev())
+        nbytes = self.lib.bore_topk_workspace_bytes(S, int(k))
+        work = torch.empty(int(nbytes), dtype=torch.uint8, device=self._tdev())
+        _lib.check(self.lib.bore_topk_smallest(_ptr(f_dev), S, int(k), 1 if negate else 0, _ptr(idx),
+                                               _ptr(work), work.numel(), self.device, self._stream()))
+        return idx
+
+    def select_best(self, fun_dev, status_dev, keep_dev=None, idx_offset=0):
+        """One int64 (device) packing the first-minimum winner; 0 if no start qualifies."""
+        torch = _torch()
+        S = fun_dev.shape[0]
+        assert fun_dev.dtype == torch.float64 and status_dev.dtype == torch.int32
+        key = torch.zeros(1, dtype=torch.int64, device=self._tdev())
+        _lib.check(self.lib.bore_select_best(_ptr(fun_dev), _ptr(status_dev), _ptr(keep_dev), S,
+                                             int(idx_offset), _ptr(key), self.device, self._stream()))
+        return key
+
+    # ------------------------------------------------------------------ K1
+    def fit_dev(self, X_dev, z_dev, N, batch_size, epochs, perm_dev, loss_dev=None,
+                model0=0, count=1, shared_data=True, shared_perm=True):
+        torch = _torch()
+        assert X_dev.dtype == torch.float32 and z_dev.dtype == torch.float32
+        assert perm_dev.dtype == torch.int32 and perm_dev.is_contiguous()
+        if loss_dev is None:
+            loss_dev = torch.empty(count, epochs, dtype=torch.float32, device=self._tdev())
+        _lib.check(self.lib.bore_mlp_fit(self.h, model0, count, _ptr(X_dev), _ptr(z_dev), int(N),
+                                         1 if shared_data else 0, int(batch_size), int(epochs),
+                                         _ptr(perm_dev), 1 if shared_perm else 0,
+                                         _ptr(loss_dev), self._stream()))
+        return loss_dev
+
+    def fit(self, X, z, epochs, batch_size, permutations, l2=None, model=0):
+        """Keras ``fit`` with explicit per-epoch permutations -> history loss (epochs,)."""
+        if l2 is not None:
+            self.set_regularizers(l2)
+        X = np.asarray(X)
+        N = X.shape[0]
+        perm = np.ascontiguousarray(permutations, np.int32).reshape(epochs, N)
+        loss = self.fit_dev(self.to_device(X, np.float32),
+                            self.to_device(np.asarray(z).astype(np.float32), np.float32),
+                            N, batch_size, epochs, self.to_device(perm, np.int32),
+                            model0=model, count=1)
+        return loss.cpu().numpy()[0]
+
+    def evaluate(self, X, z, l2=None, model=0):
+        if l2 is not None:
+            self.set_regularizers(l2)
+        X = np.asarray(X)
+        out = np.zeros(2, np.float32)
+        Xd = self.to_device(X, np.float32)
+        zd = self.to_device(np.asarray(z).astype(np.float32), np.float32)
+        _lib.check(self.lib.bore_mlp_evaluate(self.h, model, _ptr(Xd), _ptr(zd), X.shape[0],
+                                              _np_ptr(out), self._stream()))
+        return [float(out[0]), float(out[1])]
+
+
+def ffma_peak_tflops(device=0, iters=4096):
+    lib = _lib.require_cuda()
+    out = C.c_double()
+    _lib.check(lib.bore_bench_ffma_peak(int(device), int(iters), C.byref(out)))
+    return out.value

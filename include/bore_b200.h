@@ -70,6 +70,16 @@ int bore_mlp_set_adam_state(bore_mlp *h, int model, const float *m_host,
                             const float *v_host, int64_t iterations);
 int bore_mlp_get_adam_state(bore_mlp *h, int model, float *m_host, float *v_host,
                             int64_t *iterations);
+/* zero Adam's m, v and `iterations` of models [model0, model0+count) on `stream` (what
+ * re-compiling a Keras model does to its optimizer); asynchronous                         */
+int bore_mlp_reset_optimizer(bore_mlp *h, int model0, int count, void *stream);
+/* Adam hyper-parameters (keras.optimizers.Adam(learning_rate, beta_1, beta_2, epsilon));
+ * defaults are Keras' "adam": 1e-3, 0.9, 0.999, 1e-7.                                   */
+int bore_mlp_set_optimizer(bore_mlp *h, float lr, float beta1, float beta2, float eps);
+/* l2 regularisers (keras.regularizers.l2) per Dense layer: l2_kernel[l] * sum(W_l^2) +
+ * l2_bias[l] * sum(b_l^2) is added to the training loss (n_layers floats each; zeros = none).
+ * The plugin regularises its hidden layers only (plugins/hpbandster/base.py:113-116,152-155). */
+int bore_mlp_set_regularizers(bore_mlp *h, const float *l2_kernel_host, const float *l2_bias_host);
 /* device pointer of the flat parameter block [n_models][n_params] (for NCCL broadcast) */
 int bore_mlp_params_dev(bore_mlp *h, float **params_dev);
 
@@ -98,19 +108,17 @@ int bore_mlp_value_and_grad(bore_mlp *h, int model, int transform, int negate,
  *   perm_dev [count or 1][epochs][N] int32: the per-epoch shuffles (Keras draws them
  *     internally; made explicit so trajectories can be compared).  One set per model, or
  *     one shared set when `shared_perm != 0`.
- *   l2: weight of the l2(kernel)+l2(bias) regulariser (plugins/hpbandster/base.py:113-116)
  *   loss_out_dev [count][epochs] fp32: Keras' history["loss"] (sample-weighted running
  *     mean of the per-batch losses, each taken before its update); may be NULL.
  * Weights and Adam state of the handle are updated in place.                            */
 int bore_mlp_fit(bore_mlp *h, int model0, int count, const float *X_dev,
                  const float *z_dev, int N, int shared_data, int batch_size, int epochs,
-                 const int32_t *perm_dev, int shared_perm, float l2, float *loss_out_dev,
-                 void *stream);
+                 const int32_t *perm_dev, int shared_perm, float *loss_out_dev, void *stream);
 
 /* Keras Model.evaluate -> mean loss and `accuracy` (plugins/hpbandster/base.py:186).
  * out_host[0]=loss, out_host[1]=accuracy.  synchronous.                                 */
 int bore_mlp_evaluate(bore_mlp *h, int model, const float *X_dev, const float *z_dev,
-                      int N, float l2, float *out_host, void *stream);
+                      int N, float *out_host, void *stream);
 
 /* ---- K3: batched bound-constrained L-BFGS-B -------------------------------------------
  * Replaces the per-start scipy.optimize.minimize(fun, x0, method="L-BFGS-B", jac=True,
@@ -135,6 +143,13 @@ int bore_lbfgsb_minimize(bore_mlp *h, int model, int transform, const double *X0
                          int32_t *status_dev, int32_t *task_dev, int *rounds_out,
                          long long *evals_out, void *stream);
 
+/* Measurement hooks for bench.py: when enabled, bore_lbfgsb_minimize brackets every kernel it
+ * launches with CUDA events on `stream`; bore_lbfgsb_last_profile returns, for the last such
+ * call, out[0] = K2 total ms, out[1] = stepper total ms, out[2] = rounds (= launches of each
+ * kernel), out[3] = stepper algorithmic bytes, out[4] = K2 point evaluations.  */
+int bore_lbfgsb_profile(int enable);
+int bore_lbfgsb_last_profile(double *out5);
+
 /* L-BFGS-B stepper alone, objective supplied by the caller (reverse communication):
  * used to pin the on-device algorithm against SciPy's setulb request by request, and by
  * minimize_multi_start() for objectives that are not a bore_mlp.
@@ -157,13 +172,14 @@ int bore_lbfgsb_results(int S, int D, void *work_dev, double *x_dev, double *fun
 /* ---- K4: selection ---------------------------------------------------------------------
  * bore_topk_smallest replaces np.argpartition(f_init, kth=num_starts-1)
  * (bore/mixins.py:56): indices of the k smallest of f_dev[S] (ascending, ties by lower
- * index) into idx_dev[k].
+ * index) into idx_dev[k].  With negate != 0 the ranking is on -f_dev (the reference ranks
+ * f_init = -predict(X_init), bore/mixins.py:52).
  * bore_select_best replaces the final scan of bore/mixins.py:80-87: among starts with
  * status in {0,1} and keep_dev[i]!=0 (keep_dev may be NULL), the FIRST minimum of fun.
  * key_dev receives one int64: (orderable(-fun) << 31) | (0x7fffffff - (idx + idx_offset)),
  * or 0 if no start qualifies -- ready for one NCCL max all-reduce across ranks.         */
-int bore_topk_smallest(const float *f_dev, int S, int k, int32_t *idx_dev, void *work_dev,
-                       size_t work_bytes, int device, void *stream);
+int bore_topk_smallest(const float *f_dev, int S, int k, int negate, int32_t *idx_dev,
+                       void *work_dev, size_t work_bytes, int device, void *stream);
 size_t bore_topk_workspace_bytes(int S, int k);
 int bore_select_best(const double *fun_dev, const int32_t *status_dev,
                      const uint8_t *keep_dev, int S, int64_t idx_offset, int64_t *key_dev,

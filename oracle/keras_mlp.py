@@ -210,13 +210,27 @@ def loss_and_weight_grads(weights, acts, Xb, zb, l2=0.0, dtype=np.float32):
         grads[2 * l + 1] = delta.sum(axis=0)
         if l > 0:
             delta = delta @ weights[2 * l].T
-    if l2:
+    l2v = _l2_vector(l2, len(weights))
+    if any(l2v):
         reg = f(0)
         for i, w in enumerate(weights):
-            reg += f(l2) * f(np.sum(w * w, dtype=dtype))
-            grads[i] = grads[i] + f(2 * l2) * w
+            if l2v[i]:
+                reg += f(l2v[i]) * f(np.sum(w * w, dtype=dtype))
+                grads[i] = grads[i] + f(2 * l2v[i]) * w
         loss = f(loss + reg)
     return loss, grads
+
+
+def _l2_vector(l2, n):
+    """``l2`` is one factor for every kernel and bias, or a per-array sequence in Keras weight
+    order [k0, b0, k1, b1, ...] (the plugin regularises the hidden layers only:
+    plugins/hpbandster/base.py:147-155 passes the regularisers through ``layer_kws``, not
+    ``final_layer_kws``)."""
+    if np.isscalar(l2):
+        return [float(l2)] * n
+    l2 = [float(v) for v in l2]
+    assert len(l2) == n
+    return l2
 
 
 def fit(weights, acts, X, z, epochs, batch_size, permutations, adam=None, l2=0.0,

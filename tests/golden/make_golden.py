@@ -1,0 +1,125 @@
+"""Generates the committed fixtures under tests/golden/ -- run in the BUILD container only.
+
+Two sources:
+  1. the reference's own importable modules (bore.math, bore.data, bore.optimizers.utils under
+     /root/reference; numpy/scipy only) -> `host_golden.json`: known answers for the host-side
+     helpers of the path, produced by the reference code itself;
+  2. the installed SciPy L-BFGS-B (the reference's optimiser, scipy/optimize/_lbfgsb_py.py)
+     driven by the oracle MLP -> `lbfgsb_golden.npz`: per-start x*, fun, nit, nfev, status on
+     seeded problems, with the SciPy/NumPy versions recorded.
+
+/root/reference does not exist on the GPU box: tests only ever read the committed outputs.
+
+    python tests/golden/make_golden.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import scipy
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def host_golden():
+    sys.path.insert(0, "/root/reference")
+    from bore.math import steps_per_epoch, ceil_divide          # noqa: E402
+    from bore.data import Record                                 # noqa: E402
+    from bore.optimizers.utils import from_bounds                # noqa: E402
+    from scipy.optimize import Bounds
+
+    out = {"source": "ltiao/bore v1.5.0 modules imported from /root/reference",
+           "numpy": np.__version__, "scipy": scipy.__version__}
+    out["steps_per_epoch"] = [[n, b, steps_per_epoch(n, b)] for n in
+                              (1, 10, 32, 63, 64, 65, 100, 110, 127, 128, 500, 1000, 2000, 4096)
+                              for b in (1, 32, 64, 100)]
+    out["ceil_divide"] = [[a, b, int(ceil_divide(a, b))] for a in (-7, -1, 0, 1, 7, 64, 65)
+                          for b in (1, 2, 64)]
+    # from_bounds on both input kinds
+    fb = []
+    for lo, hi in (([0.0, 0.0], [1.0, 1.0]), ([-5.0, 0.0, 2.0], [10.0, 15.0, 3.0])):
+        (l1, h1), d1 = from_bounds(Bounds(np.array(lo), np.array(hi)))
+        (l2, h2), d2 = from_bounds(list(zip(lo, hi)))
+        fb.append(dict(lo=lo, hi=hi, bounds_obj=[list(map(float, l1)), list(map(float, h1)), d1],
+                       pairs=[list(map(float, l2)), list(map(float, h2)), d2]))
+    out["from_bounds"] = fb
+    # Record: quantile labelling and duplicate test
+    recs = []
+    for seed, n, gamma in ((0, 10, 0.25), (1, 37, 1 / 3), (2, 110, 0.25), (3, 8, 0.5)):
+        rs = np.random.RandomState(seed)
+        X = rs.uniform(size=(n, 3))
+        y = rs.normal(size=n)
+        y[:3] = y[0]  # ties around the threshold exercise the strict '<'
+        rec = Record()
+        for xi, yi in zip(X, y):
+            rec.append(x=xi, y=yi, b=1.0)
+        Xc, z = rec.load_classification_data(gamma)
+        probes = [X[0], X[0] + 1e-9, X[0] + 1e-4, X[-1] * (1 + 5e-6), rs.uniform(size=3)]
+        recs.append(dict(seed=seed, n=n, gamma=gamma, X=X.tolist(), y=y.tolist(),
+                         z=[bool(v) for v in z], size=rec.size(),
+                         probes=[p.tolist() for p in probes],
+                         is_duplicate=[bool(rec.is_duplicate(p)) for p in probes]))
+    out["record"] = recs
+    with open(os.path.join(HERE, "host_golden.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("host_golden.json written")
+
+
+def lbfgsb_golden():
+    from oracle import keras_mlp as km, argmax as am
+    from helpers import NETS, trained_weights
+    from scipy.optimize import Bounds
+    out = dict(scipy_version=np.array(scipy.__version__), numpy_version=np.array(np.__version__))
+    for name in ("cfg1_branin", "cfg2_hartmann6", "cfg5_plugin8", "cfg3_ackley50"):
+        dims, acts, transform = NETS[name]
+        n = dims[0]
+        w = trained_weights(dims, acts, seed=31)
+        S = 24
+        X0 = np.random.RandomState(77).uniform(size=(S, n))
+        r = am.minimize_starts(w, acts, X0, Bounds(np.zeros(n), np.ones(n)), transform=transform)
+        f0, g0 = km.value_and_input_grad(w, acts, X0, transform, True, np.float32)
+        out[name + "/X0"] = X0
+        out[name + "/f0"] = f0
+        out[name + "/g0"] = g0
+        for i, wi in enumerate(w):
+            out[f"{name}/w{i}"] = wi
+        for k, v in r.items():
+            out[f"{name}/{k}"] = v
+    np.savez_compressed(os.path.join(HERE, "lbfgsb_golden.npz"), **out)
+    print("lbfgsb_golden.npz written")
+
+
+def fit_golden():
+    """Oracle fit trajectories (restated Keras semantics) frozen so that a later change to the
+    oracle cannot silently move the target the CUDA kernel is held to."""
+    from oracle import keras_mlp as km
+    from helpers import NETS, synthetic_targets
+    out = {}
+    for name, N, E, l2 in (("cfg1_branin", 110, 30, 0.0), ("cfg5_plugin8", 200, 12, 1e-3)):
+        dims, acts, _ = NETS[name]
+        rs = np.random.RandomState(5)
+        X = rs.uniform(size=(N, dims[0]))
+        y = synthetic_targets(X)
+        z = y < np.quantile(y, 0.25)
+        perms = np.stack([rs.permutation(N) for _ in range(E)])
+        w = km.init_weights(dims, 9)
+        out[name + "/w0"] = np.concatenate([a.ravel() for a in w])
+        hist, adam = km.fit(w, acts, X, z, E, 64, perms, l2=l2)
+        out[name + "/X"] = X
+        out[name + "/z"] = z
+        out[name + "/perms"] = perms
+        out[name + "/loss"] = hist
+        out[name + "/w_final"] = np.concatenate([a.ravel() for a in w])
+        out[name + "/l2"] = np.array(l2)
+    np.savez_compressed(os.path.join(HERE, "fit_golden.npz"), **out)
+    print("fit_golden.npz written")
+
+
+if __name__ == "__main__":
+    host_golden()
+    lbfgsb_golden()
+    fit_golden()

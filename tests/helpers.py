@@ -1,0 +1,36 @@
+"""Shared synthetic problems for the parity tests (seeded, oracle-sized)."""
+import numpy as np
+
+from oracle import keras_mlp as km
+
+# (name, dims, activations, transform) -- the BASELINE.json configs' networks
+NETS = {
+    "cfg1_branin": ([2, 16, 16, 1], ["relu", "relu", "sigmoid"], "identity"),
+    "cfg2_hartmann6": ([6, 32, 32, 1], ["relu", "relu", "sigmoid"], "identity"),
+    "cfg3_ackley50": ([50, 64, 64, 64, 1], ["relu", "relu", "relu", "sigmoid"], "identity"),
+    "cfg5_plugin8": ([8, 32, 32, 32, 1], ["elu", "elu", "elu", "linear"], "sigmoid"),
+    "ref_test_linear": ([2, 32, 32, 32, 1], ["linear"] * 4, "identity"),
+    "tanh_exp": ([5, 24, 40, 1], ["tanh", "sigmoid", "linear"], "exp"),
+    "no_hidden": ([7, 1], ["sigmoid"], "identity"),
+}
+
+
+def synthetic_targets(X):
+    """Smooth multimodal test objective on the unit cube (stand-in for Branin/Hartmann/Ackley)."""
+    return np.sum((X - 0.4) ** 2, axis=1) + 0.1 * np.sin(5.0 * X[:, 0]) * np.cos(3.0 * X[:, -1])
+
+
+def trained_weights(dims, acts, seed=0, N=300, epochs=30, gamma=0.25):
+    """Glorot init + a short oracle fit on quantile-labelled data: realistic, non-degenerate
+    weights for value/gradient/argmax parity."""
+    rs = np.random.RandomState(seed)
+    w = km.init_weights(dims, seed)
+    X = rs.uniform(size=(N, dims[0]))
+    y = synthetic_targets(X)
+    z = y < np.quantile(y, gamma)
+    perms = np.array([rs.permutation(N) for _ in range(epochs)])
+    acts_fit = list(acts)
+    if acts_fit[-1] not in ("sigmoid", "linear"):
+        acts_fit[-1] = "linear"
+    km.fit(w, acts_fit, X, z, epochs, 64, perms)
+    return w

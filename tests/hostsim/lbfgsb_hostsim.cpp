@@ -61,7 +61,8 @@ int hs_step(void *p, double f, const double *g, double *xreq) {
   const int n = h->P.n;
   h->s.f = f;
   memcpy(h->w.g, g, n * sizeof(double));
-  const int pend = lb_advance(h->P, h->w, h->s);
+  LbNoMem nomem;
+  const int pend = lb_advance(h->P, h->w, h->s, nomem);
   if (pend) {
     bool same = true;
     for (int i = 0; i < n; ++i) same = same && (h->w.x[i] == h->xlast[i]);

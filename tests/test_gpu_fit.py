@@ -1,0 +1,114 @@
+"""K1 parity: fused CUDA training vs the NumPy restatement of Keras fit (oracle/keras_mlp.py).
+
+north_star: "Training loss trajectories must agree within 1e-4, given identical init weights
+and minibatch permutations."  (The oracle itself is a restatement -- TF is not installable --
+so this is parity with the restated Keras semantics; see oracle/__init__.py.)
+"""
+import numpy as np
+import pytest
+
+from oracle import keras_mlp as km
+from helpers import NETS, synthetic_targets
+
+pytestmark = pytest.mark.gpu
+
+LOSS_TOL = 1e-4
+
+
+def _problem(dims, N, epochs, seed):
+    rs = np.random.RandomState(seed)
+    X = rs.uniform(size=(N, dims[0]))
+    y = synthetic_targets(X)
+    z = y < np.quantile(y, 0.25)
+    perms = np.stack([rs.permutation(N) for _ in range(epochs)])
+    return X, z, perms
+
+
+CASES = [
+    # name, N, epochs, batch, l2
+    ("cfg1_branin", 110, 60, 64, 0.0),      # README: 2 steps/epoch, ragged last batch of 46
+    ("cfg1_branin", 10, 30, 64, 0.0),       # N < batch
+    ("cfg2_hartmann6", 500, 25, 64, 0.0),   # last batch of 52
+    ("cfg3_ackley50", 2000, 4, 64, 0.0),    # last batch of 16
+    ("cfg5_plugin8", 333, 20, 64, 0.0),     # plugin form: elu + logits
+    ("cfg5_plugin8", 333, 20, 64, 1e-3),    # + l2 on every kernel and bias
+    ("cfg5_plugin8", 333, 20, 64, [1e-3] * 6 + [0.0, 0.0]),  # plugin: hidden layers only
+    ("cfg2_hartmann6", 128, 10, 32, 0.0),   # exact multiple, other batch size
+    ("cfg2_hartmann6", 65, 10, 64, 0.0),    # last batch of ONE sample
+]
+
+
+@pytest.mark.parametrize("name,N,epochs,batch,l2", CASES)
+def test_fit_loss_trajectory_matches_oracle(name, N, epochs, batch, l2):
+    from bore_b200.engine import NativeMLP
+    dims, acts, _ = NETS[name]
+    X, z, perms = _problem(dims, N, epochs, seed=N + epochs)
+    net_l2 = l2 if l2 else None
+    w0 = km.init_weights(dims, 3)
+    w_ref = [w.copy() for w in w0]
+    hist_ref, adam_ref = km.fit(w_ref, acts, X, z, epochs, batch, perms, l2=l2)
+
+    net = NativeMLP(dims, acts)
+    net.set_weights(w0)
+    hist = net.fit(X, z, epochs, batch, perms, l2=l2)
+    assert hist.shape == (epochs,)
+    assert np.abs(hist - hist_ref).max() <= LOSS_TOL, np.abs(hist - hist_ref).max()
+    # the trained weights track too (fp32 summation-order noise amplified by Adam)
+    for a, b in zip(net.get_weights(), w_ref):
+        assert np.abs(a - b).max() <= 2e-3, np.abs(a - b).max()
+    m, v, t = net.get_adam_state()
+    assert t == adam_ref.t == epochs * (-(-N // batch))
+    for a, b in zip(m, adam_ref.m):
+        assert np.abs(a - b).max() <= 1e-4
+    # evaluate() = loss/accuracy of the final weights
+    loss, acc = net.evaluate(X, z, l2=l2)
+    loss_ref, acc_ref = km.evaluate(net.get_weights(), acts, X, z, l2=l2)
+    assert abs(loss - loss_ref) <= 1e-5 and abs(acc - acc_ref) <= 1e-6
+
+
+def test_adam_state_persists_across_fit_calls():
+    """Two fits of E epochs == one fit of 2E epochs (README.rst:93 refits the same model)."""
+    from bore_b200.engine import NativeMLP
+    dims, acts, _ = NETS["cfg2_hartmann6"]
+    X, z, perms = _problem(dims, 200, 12, seed=1)
+    w0 = km.init_weights(dims, 0)
+    a = NativeMLP(dims, acts); a.set_weights(w0)
+    h_all = a.fit(X, z, 12, 64, perms)
+    b = NativeMLP(dims, acts); b.set_weights(w0)
+    h1 = b.fit(X, z, 6, 64, perms[:6])
+    h2 = b.fit(X, z, 6, 64, perms[6:])
+    assert np.array_equal(np.concatenate([h1, h2]), h_all)
+    for u, v in zip(a.get_weights(), b.get_weights()):
+        assert np.array_equal(u, v)
+    # and a state transplanted through get/set continues identically
+    c = NativeMLP(dims, acts); c.set_weights(w0)
+    c.fit(X, z, 6, 64, perms[:6])
+    d = NativeMLP(dims, acts); d.set_weights(c.get_weights()); d.set_adam_state(*c.get_adam_state())
+    assert np.array_equal(d.fit(X, z, 6, 64, perms[6:]), h2)
+
+
+def test_many_models_one_launch():
+    """M independent classifiers (seeds / BO problems) trained by one launch, one CTA each."""
+    import torch
+    from bore_b200.engine import NativeMLP
+    dims, acts, _ = NETS["cfg2_hartmann6"]
+    M, N, E = 7, 150, 8
+    probs = [_problem(dims, N, E, seed=10 + i) for i in range(M)]
+    ws = [km.init_weights(dims, i) for i in range(M)]
+    net = NativeMLP(dims, acts, n_models=M)
+    for i, w in enumerate(ws):
+        net.set_weights(w, model=i)
+    Xd = net.to_device(np.concatenate([p[0] for p in probs]), np.float32)
+    zd = net.to_device(np.concatenate([p[1] for p in probs]).astype(np.float32), np.float32)
+    pd = net.to_device(np.stack([p[2] for p in probs]).astype(np.int32), np.int32)
+    loss = net.fit_dev(Xd, zd, N, 64, E, pd, model0=0, count=M, shared_data=False,
+                       shared_perm=False).cpu().numpy()
+    for i in range(M):
+        solo = NativeMLP(dims, acts); solo.set_weights(ws[i])
+        h = solo.fit(*probs[i][:2], E, 64, probs[i][2])
+        assert np.array_equal(h, loss[i])
+        for u, v in zip(solo.get_weights(), net.get_weights(model=i)):
+            assert np.array_equal(u, v)
+        w_ref = [w.copy() for w in ws[i]]
+        h_ref, _ = km.fit(w_ref, acts, *probs[i][:2], E, 64, probs[i][2])
+        assert np.abs(loss[i] - h_ref).max() <= LOSS_TOL
