@@ -1013,7 +1013,17 @@ LB_HD int lb_advance(const LbParams &P, LbWork &w, LbScal &s, Mem &mem) {
       } else {
         LB_SYNC();
         if (s.stp == 1.0) { LB_FOR(i, n) w.x[i] = w.z[i]; }
-        else { LB_FOR(i, n) w.x[i] = s.stp * w.d[i] + w.t[i]; }
+        else {
+          // SciPy's lnsrlb also clamps the trial point into the box, so that rounding in
+          // stp*d + xold cannot step outside (scipy/optimize/tests/test_lbfgsb_setulb.py:70-113)
+          LB_FOR(i, n) {
+            double xi = s.stp * w.d[i] + w.t[i];
+            const int nb = P.nbd[i];
+            if (nb == 1 || nb == 2) xi = fmax(xi, P.lo[i]);
+            if (nb == 2 || nb == 3) xi = fmin(xi, P.hi[i]);
+            w.x[i] = xi;
+          }
+        }
         LB_SYNC();
         s.phase = LB_PH_LNSRCH;
         return 1;

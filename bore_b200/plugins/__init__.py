@@ -1,0 +1,1 @@
+"""Host-framework plugins that call the hot path (bore/plugins/)."""

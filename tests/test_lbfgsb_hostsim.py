@@ -124,3 +124,45 @@ def test_maxiter_status(hs):
     got, ref = _run(hs, w, acts, transform, X0, np.zeros(50), np.ones(50), maxiter=2)
     assert np.array_equal(got["status"], ref["status"]) and np.array_equal(got["nit"], ref["nit"])
     assert np.any(got["status"] == 1)
+
+
+def test_scipy_bound_violation_regression(hs):
+    """SciPy's own known-answer for this path (scipy/optimize/tests/test_lbfgsb_setulb.py:70-113):
+    7 setulb steps on a tabulated objective that used to step outside [0,1] by rounding.  Our
+    stepper must request the same points as setulb, all of them feasible."""
+    from scipy.optimize import _lbfgsb
+    from scipy.optimize.tests.test_lbfgsb_setulb import objfun
+    n, m = 5, 10
+    lo, hi = np.zeros(n), np.ones(n)
+    x0 = np.array([0.8750000000000278, 0.7500000000000153, 0.9499999999999722,
+                   0.8214285714285992, 0.6363636363636085])
+    # setulb side
+    idt = np.int32
+    x = x0.copy()
+    nbd = np.full(n, 2, idt)
+    wa = np.zeros(2 * m * n + 5 * n + 11 * m * m + 8 * m)
+    iwa, task, ln_task = np.zeros(3 * n, idt), np.zeros(2, idt), np.zeros(2, idt)
+    lsave, isave, dsave = np.zeros(4, idt), np.zeros(44, idt), np.zeros(29)
+    ref_requests = []
+    for _ in range(7):
+        f, g = objfun(x)
+        try:
+            _lbfgsb.setulb(m, x, lo, hi, nbd, f, g, 1e7, 1e-5, wa, iwa, task, lsave, isave, dsave,
+                           20, ln_task)
+        except TypeError:
+            pytest.skip("this SciPy's setulb has a different signature")
+        if task[0] == 3:
+            ref_requests.append(x.copy())
+    # our side: same factr*epsmch, identical tabulated f,g
+    h = hs.hs_create(n, m, _P(lo), _P(hi), 1e7 * np.finfo(float).eps, 1e-5, 1000, 15000, 20)
+    xr = np.zeros(n)
+    hs.hs_start(h, _P(x0.copy()), _P(xr))
+    ours = [xr.copy()]
+    for _ in range(len(ref_requests) - 1):
+        f, g = objfun(xr)
+        assert hs.hs_step(h, float(f), _P(np.ascontiguousarray(g, np.float64)), _P(xr)) == 1
+        ours.append(xr.copy())
+    hs.hs_destroy(h)
+    for a, b in zip(ours, ref_requests):
+        assert np.all(a >= lo) and np.all(a <= hi)
+        np.testing.assert_allclose(a, b, rtol=0, atol=1e-12)
