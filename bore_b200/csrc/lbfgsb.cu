@@ -5,28 +5,44 @@
 //
 //     round r:   K2 (mlp_eval.cu) evaluates f,g for every start still asking for it, read
 //                through a compacted active list;
-//                lbfgsb_step_kernel: one WARP per active start consumes f,g and runs the
-//                L-BFGS-B state machine of lbfgsb_core.h (Cauchy point, subspace
-//                minimisation, More'-Thuente line search, BFGS update) until the start
-//                either terminates or posts its next trial point, appending itself to the
-//                next round's active list.
+//                the stepper consumes f,g and runs the L-BFGS-B state machine of
+//                lbfgsb_core.h (Cauchy point, subspace minimisation, More'-Thuente line
+//                search, BFGS update) for every active start until it either terminates or
+//                posts its next trial point, appending itself to the next round's list.
 //
-// Finished starts drop out of the list, so late rounds cost only as much as the few starts
-// that are still running (the per-start evaluation counts vary by >10x).
-// The host only polls the active counter, pipelined one chunk of rounds behind the launches.
+// lbfgsb_warp_kernel: one WARP per active start, the start's state staged in shared memory
+// (variant 1 of lbfgsb_core.h).  Finished starts drop out of the list, so late rounds cost
+// only as much as the few starts that are still running (the per-start evaluation counts vary
+// by >10x) -- and since such a round is a handful of warps, its cost is the
+// LATENCY of one step, which is why a start gets a whole warp.  The host only polls the
+// active counter, pipelined one chunk of rounds behind the launches.
 //
-// State.  Per start, a contiguous block in HBM: scalars | xold gold d z | W=[Y S] (n x (2m+1))
-// | SY SS WT.  A step loads only what it touches: a step that just continues a line search
-// reads the scalars and 4 vectors; the matrices are streamed into shared memory only when a
-// new iteration starts, and written back only after a BFGS update.
+// State.  Per start, a contiguous block in HBM: scalars (LbScal, 256 B) | xold gold d z (4n)
+// | W = [Y S] (n x (2m+1)) | SY SS YY Tinv (4 m^2) doubles.  A step loads only what it
+// touches: a step that just continues a line search reads the scalars and 4 vectors; the
+// matrices are streamed into shared memory only when a new iteration starts, and written back
+// only after a BFGS update.
+//
+// Tried and rejected (round 1, measured on B200, cfg 3): one THREAD per start with the state
+// read in place from a structure-of-arrays block and the small dense scratch in local memory.
+// Correct (same source compiled serially), but a heavy step is ~10^5 dependent instructions
+// on L2-latency operands: 8-10 ms per round regardless of how many starts are active, against
+// 4.7 ms for 65,536 starts with the warp kernel.  profiles/r01_notes.md has the launch list.
+#include <float.h>
+#include <math.h>
 #include <string.h>
 
 #include <algorithm>
 #include <cmath>
 
 #include "common.cuh"
-#include "lbfgsb_core.h"
+#include "lbfgsb_types.h"
 
+namespace lbw {  // warp-collective variant
+#define LB_VARIANT 1
+#include "lbfgsb_core.h"
+#undef LB_VARIANT
+}  // namespace lbw
 namespace {
 
 constexpr int SCAL_BYTES = 256;
@@ -34,12 +50,12 @@ static_assert(sizeof(LbScal) <= SCAL_BYTES, "LbScal grew past its slot");
 
 struct LbLayout {
   // offsets in bytes from the workspace base
-  size_t lo, hi, nbd, cnt, evals, lists, xf, f, g, pend, blocks, block_stride, xreq, total;
+  size_t lo, hi, nbd, cnt, evals, lists, xf, f, g, blocks, block_stride, total;
 };
 
 __host__ __device__ inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
-inline LbLayout make_layout(int S, int n, int m, bool own_xreq) {
+inline LbLayout make_layout(int S, int n, int m) {
   LbLayout L;
   size_t o = 0;
   L.lo = o; o += align_up(n * sizeof(double), 16);
@@ -51,11 +67,10 @@ inline LbLayout make_layout(int S, int n, int m, bool own_xreq) {
   L.xf = o; o += align_up((size_t)S * n * sizeof(float), 16);
   L.f = o; o += align_up((size_t)S * sizeof(float), 16);
   L.g = o; o += align_up((size_t)S * n * sizeof(float), 16);
-  L.pend = o; o += align_up((size_t)S * sizeof(int), 16);
-  L.block_stride = align_up(SCAL_BYTES + ((size_t)4 * n + (size_t)n * LB_LDW(m) + 3 * m * m) *
-                                             sizeof(double), 16);
+  o = align_up(o, 256);
+  L.block_stride = align_up(SCAL_BYTES + ((size_t)4 * n + (size_t)n * LB_LDW(m) +
+                                          LB_NPERSIST_MM * m * m) * sizeof(double), 128);
   L.blocks = o; o += L.block_stride * S;
-  L.xreq = o; if (own_xreq) o += align_up((size_t)S * n * sizeof(double), 16);
   L.total = o;
   return L;
 }
@@ -63,7 +78,7 @@ inline LbLayout make_layout(int S, int n, int m, bool own_xreq) {
 struct LbDev {
   LbParams P;
   int S;
-  char *blocks;
+  char *blocks;   // [S] per-start state blocks
   size_t block_stride;
   double *xreq;   // [S][n] last requested point (final x once a start is done)
   float *xf;      // [S][n] fp32 copy of the request for the MLP kernel (may be NULL)
@@ -76,39 +91,29 @@ struct LbDev {
   int *pend;      // [S] (may be NULL)
 };
 
-// lazy loader of the limited-memory matrices (global block -> the warp's smem workspace)
-struct BlockMem {
-  const LbParams &P;
-  LbWork &w;
-  LbScal &s;
-  double *gW, *gM;  // global W and [sy ss wt]
-  bool loaded = false, is_dirty = false, vec_dirty = false;
-  __host__ __device__ BlockMem(const LbParams &P_, LbWork &w_, LbScal &s_, double *gW_, double *gM_)
-      : P(P_), w(w_), s(s_), gW(gW_), gM(gM_) {}
-  __host__ __device__ void load() {
-    if (loaded) return;
-    loaded = true;
-    if (s.col == 0) return;  // empty memory: nothing valid to read
-    const int nW = P.n * LB_LDW(P.m), nM = 3 * P.m * P.m;
-    for (int i = LB_LANE; i < nW; i += 32) w.W[i] = gW[i];
-    for (int i = LB_LANE; i < nM; i += 32) w.sy[i] = gM[i];  // sy, ss, wt are contiguous
-    LB_SYNC();
-  }
-  __host__ __device__ void dirty() { is_dirty = true; }
-  __host__ __device__ void dirty_vec() { vec_dirty = true; }
-  __host__ __device__ void store() {
-    if (!is_dirty) return;
-    const int nW = P.n * LB_LDW(P.m), nM = 3 * P.m * P.m;
-    LB_SYNC();
-    for (int i = LB_LANE; i < nW; i += 32) gW[i] = w.W[i];
-    for (int i = LB_LANE; i < nM; i += 32) gM[i] = w.sy[i];
-  }
-};
+__device__ __forceinline__ LbScal *scal_of(const LbDev &D, int sid) {
+  return reinterpret_cast<LbScal *>(D.blocks + D.block_stride * sid);
+}
 
 __device__ __forceinline__ int init_iwhere(const LbParams &P, int i) {
   const int nb = P.nbd[i];
   if (nb == 0) return -1;
   return (nb == 2 && P.hi[i] - P.lo[i] <= 0.0) ? 3 : 0;
+}
+
+// algorithmic bytes of one step: what an ideal implementation has to move --
+// scalars r+w, f, g and x read, the four vectors if a line search is in flight, the valid
+// part of the limited memory when a new iteration starts, and what changed on the way out
+__device__ __forceinline__ unsigned long long step_bytes(int n, int fg_size, bool was_ls,
+                                                         bool heavy, int col_in, int col_out,
+                                                         bool pend, bool updated) {
+  unsigned long long b = 2ull * sizeof(LbScal) + (unsigned long long)fg_size * (1 + n) + 8ull * n;
+  if (was_ls) b += 32ull * n;
+  if (heavy && col_in > 0) b += 16ull * n * col_in + 32ull * col_in * col_in;
+  b += pend ? 12ull * n : 8ull * n;
+  if (heavy && pend) b += 32ull * n;
+  if (updated) b += 16ull * n + 48ull * col_out + 8ull * col_out * col_out;
+  return b;
 }
 
 // ---------------------------------------------------------------- init: one warp per start
@@ -143,17 +148,49 @@ __global__ void __launch_bounds__(128) lbfgsb_init_kernel(LbDev D, const double 
       s.nfev = 1;  // the evaluation at x0
       s.ifun = 0; s.iback = 0; s.updatd = 0; s.status = -1; s.task = 0;
       s.brackt = 0; s.stage = 0; s.ls_task = LB_LS_START; s.nskip = 0; s.nintol = 0;
-      *reinterpret_cast<LbScal *>(D.blocks + D.block_stride * sid) = s;
+      s.resume = 0;
+      *scal_of(D, sid) = s;
       D.lists[sid] = sid;
       if (D.pend) D.pend[sid] = 1;
     }
   }
 }
 
-// ---------------------------------------------------------------- one lock-step round
+// ---------------------------------------------------------------- warp variant: one round
+// lazy loader of the limited-memory matrices (state block -> the warp's smem workspace)
+struct BlockMem {
+  const LbParams &P;
+  lbw::LbWork &w;
+  LbScal &s;
+  double *gW, *gM;  // this start's W and [sy ss yy tinv] in HBM
+  bool loaded = false, is_dirty = false, vec_dirty = false;
+  __device__ BlockMem(const LbParams &P_, lbw::LbWork &w_, LbScal &s_, double *gW_, double *gM_)
+      : P(P_), w(w_), s(s_), gW(gW_), gM(gM_) {}
+  __device__ void load() {
+    if (loaded) return;
+    loaded = true;
+    if (s.col == 0) return;  // empty memory: nothing valid to read
+    const int lane = threadIdx.x & 31;
+    const int nW = P.n * LB_LDW(P.m), nM = LB_NPERSIST_MM * P.m * P.m;
+    for (int i = lane; i < nW; i += 32) w.W[i] = gW[i];
+    for (int i = lane; i < nM; i += 32) w.sy[i] = gM[i];  // sy, ss, yy, tinv contiguous
+    __syncwarp();
+    lbw::lb_prep_ld(w, P.m, s.col);
+  }
+  __device__ void dirty() { is_dirty = true; }
+  __device__ void dirty_vec() { vec_dirty = true; }
+  __device__ void store() {
+    if (!is_dirty) return;
+    const int lane = threadIdx.x & 31;
+    const int nW = P.n * LB_LDW(P.m), nM = LB_NPERSIST_MM * P.m * P.m;
+    __syncwarp();
+    for (int i = lane; i < nW; i += 32) gW[i] = w.W[i];
+    for (int i = lane; i < nM; i += 32) gM[i] = w.sy[i];
+  }
+};
+
 template <typename FG>
-__global__ void __launch_bounds__(128)
-lbfgsb_step_kernel(LbDev D, int round, size_t warp_bytes) {
+__global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t warp_bytes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = D.P.n, m = D.P.m;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -165,17 +202,16 @@ lbfgsb_step_kernel(LbDev D, int round, size_t warp_bytes) {
   int *list_nxt = D.lists + (size_t)((round + 1) & 1) * D.S;
 
   unsigned char *base = smem_raw + warp_bytes * wib;
-  LbWork w;
-  lb_carve(w, reinterpret_cast<double *>(base),
-           reinterpret_cast<int *>(base + lb_work_doubles(n, m) * sizeof(double)), n, m);
+  lbw::LbWork w;
+  lbw::lb_carve(w, reinterpret_cast<double *>(base),
+                reinterpret_cast<int *>(base + lbw::lb_work_doubles(n, m) * sizeof(double)), n, m);
   const FG *F = static_cast<const FG *>(D.F);
   const FG *G = static_cast<const FG *>(D.G);
 
   for (int idx = blockIdx.x * wpb + wib; idx < n_active; idx += gridDim.x * wpb) {
     const int sid = list_cur[idx];
-    char *blk = D.blocks + D.block_stride * sid;
-    LbScal s = *reinterpret_cast<const LbScal *>(blk);
-    double *gvec = reinterpret_cast<double *>(blk + SCAL_BYTES);
+    LbScal s = *scal_of(D, sid);
+    double *gvec = reinterpret_cast<double *>(D.blocks + D.block_stride * sid + SCAL_BYTES);
     double *gW = gvec + 4 * n;
     double *gM = gW + (size_t)n * LB_LDW(m);
     double *xr = D.xreq + (size_t)sid * n;
@@ -198,21 +234,11 @@ lbfgsb_step_kernel(LbDev D, int round, size_t warp_bytes) {
     BlockMem mem(D.P, w, s, gW, gM);
     const int col_in = s.col;
     const bool was_ls = s.phase == LB_PH_LNSRCH;
-    const int pend = lb_advance(D.P, w, s, mem);
+    const int pend = lbw::lb_advance(D.P, w, s, mem);
     __syncwarp();
-    if (lane == 0) {
-      // algorithmic traffic of this step: scalars r+w, f, g, x read; the 4 vectors if a line
-      // search was in flight; the valid part of the memory if a new iteration started; then
-      // what changed: request (fp64 + fp32 copy), the 4 vectors, the new (s,y) pair with its
-      // SY row / SS column and the refactored WT
-      unsigned long long b = 2 * sizeof(LbScal) + sizeof(FG) * (1 + n) + 8ull * n;
-      if (was_ls) b += 32ull * n;
-      if (mem.loaded && col_in > 0) b += 16ull * n * col_in + 24ull * col_in * col_in;
-      if (pend) b += 12ull * n; else b += 8ull * n;
-      if (pend && mem.vec_dirty) b += 32ull * n;
-      if (mem.is_dirty) b += 16ull * n + 16ull * s.col + 8ull * s.col * s.col;
-      atomicAdd(D.bytes, b);
-    }
+    if (lane == 0)
+      atomicAdd(D.bytes, step_bytes(n, (int)sizeof(FG), was_ls, mem.loaded, col_in, s.col,
+                                    pend != 0, mem.is_dirty));
     if (pend) {
       int changed = 0;
       for (int i = lane; i < n; i += 32) {
@@ -240,7 +266,7 @@ lbfgsb_step_kernel(LbDev D, int round, size_t warp_bytes) {
       for (int i = lane; i < n; i += 32) xr[i] = w.x[i];  // final iterate
     }
     if (lane == 0) {
-      *reinterpret_cast<LbScal *>(blk) = s;
+      *scal_of(D, sid) = s;
       if (D.pend) D.pend[sid] = pend;
     }
     __syncwarp();
@@ -251,7 +277,7 @@ __global__ void lbfgsb_results_kernel(LbDev D, double *x, double *fun, int *nit,
                                       int *status, int *task) {
   const int n = D.P.n;
   for (int sid = blockIdx.x * blockDim.x + threadIdx.x; sid < D.S; sid += gridDim.x * blockDim.x) {
-    const LbScal *s = reinterpret_cast<const LbScal *>(D.blocks + D.block_stride * sid);
+    const LbScal *s = scal_of(D, sid);
     if (fun) fun[sid] = s->f;
     if (nit) nit[sid] = s->nit;
     if (nfev) nfev[sid] = s->nfev;
@@ -286,22 +312,23 @@ struct StepLaunch {
 };
 
 int plan_step(int S, int n, int m, int sm_count, StepLaunch &L) {
-  L.warp_bytes = align_up(lb_work_doubles(n, m) * sizeof(double) + lb_work_ints(n) * sizeof(int), 16);
+  L.warp_bytes = align_up(lbw::lb_work_doubles(n, m) * sizeof(double) + lbw::lb_work_ints(n) * sizeof(int), 16);
   const size_t max_smem = 227 * 1024;
   BORE_CHECK(L.warp_bytes <= max_smem, "lbfgsb: n=%d needs %zu B of shared memory per start", n,
              L.warp_bytes);
-  int wpb = 4;
-  while (wpb > 1 && wpb * L.warp_bytes > max_smem) --wpb;
-  // prefer several small CTAs per SM over one large one
-  while (wpb > 1 && (max_smem / (wpb * L.warp_bytes + 1024)) < 2 &&
-         (max_smem / ((wpb - 1) * L.warp_bytes + 1024)) * (wpb - 1) >=
-             (max_smem / (wpb * L.warp_bytes + 1024)) * wpb)
-    --wpb;
+  // warps per CTA: whatever packs the most starts into an SM's shared memory (1 KB per CTA is
+  // reserved by the system); ties go to the larger CTA
+  int wpb = 1, best = 0;
+  for (int c = 1; c <= 4; ++c) {
+    if (c * L.warp_bytes > max_smem) break;
+    const int per_sm = (int)(max_smem / (c * L.warp_bytes + 1024)) * c;
+    if (per_sm >= best) { best = per_sm; wpb = c; }
+  }
   L.block = wpb * 32;
   L.smem = wpb * L.warp_bytes;
   int per_sm = (int)(max_smem / (L.smem + 1024));
   if (per_sm < 1) per_sm = 1;
-  if (per_sm * wpb > 32) per_sm = 32 / wpb;
+  if (per_sm * wpb > 12) per_sm = std::max(1, 12 / wpb);  // 168 registers per thread
   L.grid = sm_count * per_sm;
   const int need = (S + wpb - 1) / wpb;
   if (L.grid > need) L.grid = need;
@@ -344,6 +371,20 @@ int setup_params(LbDev &D, const LbLayout &L, char *work, int S, int n, int m, c
   return 0;
 }
 
+// one round of the stepper
+template <typename FG>
+int launch_round(const LbDev &D, const StepLaunch &SL, int round, cudaStream_t stream) {
+  static bool attr_done[2] = {false, false};
+  const int which = sizeof(FG) == 8;
+  if (!attr_done[which]) {  // opt in to > 48 KB of dynamic shared memory (once per kernel)
+    BORE_CUDA(cudaFuncSetAttribute(lbfgsb_warp_kernel<FG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   227 * 1024));
+    attr_done[which] = true;
+  }
+  lbfgsb_warp_kernel<FG><<<SL.grid, SL.block, SL.smem, stream>>>(D, round, SL.warp_bytes);
+  return 0;
+}
+
 // header kept at the very start of the external-API workspace so step/results can find things
 struct ExtHeader {
   LbDev D;
@@ -368,7 +409,7 @@ extern "C" {
 
 size_t bore_lbfgsb_workspace_bytes(int S, int D, int m) {
   if (S < 1 || D < 1 || m < 1) return 0;
-  return EXT_HDR + make_layout(S, D, m, false).total;
+  return EXT_HDR + make_layout(S, D, m).total;
 }
 
 int bore_lbfgsb_minimize(bore_mlp *h, int model, int transform, const double *X0_dev, int S,
@@ -385,7 +426,7 @@ int bore_lbfgsb_minimize(bore_mlp *h, int model, int transform, const double *X0
   BORE_CHECK(x_dev && X0_dev && work_dev, "NULL buffer");
   BORE_CUDA(cudaSetDevice(h->device));
   cudaStream_t stream = (cudaStream_t)stream_;
-  const LbLayout L = make_layout(S, n, m, false);
+  const LbLayout L = make_layout(S, n, m);
   BORE_CHECK(work_bytes >= EXT_HDR + L.total, "lbfgsb workspace too small: %zu < %zu", work_bytes,
              EXT_HDR + L.total);
   char *work = static_cast<char *>(work_dev) + EXT_HDR;
@@ -400,8 +441,6 @@ int bore_lbfgsb_minimize(bore_mlp *h, int model, int transform, const double *X0
   D.pend = nullptr;
   StepLaunch SL;
   if (plan_step(S, n, m, h->sm_count, SL)) return -1;
-  BORE_CUDA(cudaFuncSetAttribute(lbfgsb_step_kernel<float>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL.smem));
   {
     const int blocks = std::min((S + 3) / 4, h->sm_count * 8);
     lbfgsb_init_kernel<<<blocks, 128, 0, stream>>>(D, X0_dev);
@@ -425,11 +464,12 @@ int bore_lbfgsb_minimize(bore_mlp *h, int model, int transform, const double *X0
       rc = launch_mlp_eval(h, model, true, transform, 1, D.xf, S, F, G, list, D.cnt + round % 3, stream);
       if (rc) break;
       if (g_prof.enabled) cudaEventRecord(g_prof.get(3 * (size_t)round + 1), stream);
-      lbfgsb_step_kernel<float><<<SL.grid, SL.block, SL.smem, stream>>>(D, round, SL.warp_bytes);
+      rc = launch_round<float>(D, SL, round, stream);
+      if (rc) break;
       if (g_prof.enabled) cudaEventRecord(g_prof.get(3 * (size_t)round + 2), stream);
     }
     if (rc) break;
-    if (cudaGetLastError() != cudaSuccess) { bore_set_error("lbfgsb_step_kernel launch failed"); rc = -2; break; }
+    if (cudaGetLastError() != cudaSuccess) { bore_set_error("lbfgsb stepper launch failed"); rc = -2; break; }
     cudaMemcpyAsync(&cnt_host[slot], D.cnt + round % 3, sizeof(int), cudaMemcpyDeviceToHost, stream);
     cudaEventRecord(ev[slot], stream);
     if (have_prev) {
@@ -500,7 +540,7 @@ int bore_lbfgsb_init(const double *X0_dev, int S, int n, const double *lo_host,
   BORE_CHECK(bore_device_count() > 0, "no CUDA device visible -- bore_b200 has no CPU fallback");
   BORE_CUDA(cudaSetDevice(device));
   cudaStream_t stream = (cudaStream_t)stream_;
-  const LbLayout L = make_layout(S, n, m, false);
+  const LbLayout L = make_layout(S, n, m);
   BORE_CHECK(work_bytes >= EXT_HDR + L.total, "lbfgsb workspace too small: %zu < %zu", work_bytes,
              EXT_HDR + L.total);
   char *work = static_cast<char *>(work_dev) + EXT_HDR;
@@ -539,15 +579,9 @@ int bore_lbfgsb_step(const void *f_dev, const void *g_dev, int fg_is_f64, int S,
   H.D.xreq = xreq_dev; H.D.pend = pend_dev;
   StepLaunch SL;
   if (plan_step(S, n, H.D.P.m, H.sm_count, SL)) return -1;
-  if (fg_is_f64) {
-    BORE_CUDA(cudaFuncSetAttribute(lbfgsb_step_kernel<double>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL.smem));
-    lbfgsb_step_kernel<double><<<SL.grid, SL.block, SL.smem, stream>>>(H.D, H.round, SL.warp_bytes);
-  } else {
-    BORE_CUDA(cudaFuncSetAttribute(lbfgsb_step_kernel<float>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL.smem));
-    lbfgsb_step_kernel<float><<<SL.grid, SL.block, SL.smem, stream>>>(H.D, H.round, SL.warp_bytes);
-  }
+  const int rc = fg_is_f64 ? launch_round<double>(H.D, SL, H.round, stream)
+                           : launch_round<float>(H.D, SL, H.round, stream);
+  if (rc) return rc;
   BORE_CUDA(cudaGetLastError());
   H.round += 1;
   int pending = 0;

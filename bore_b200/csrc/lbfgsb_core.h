@@ -1,4 +1,4 @@
-// L-BFGS-B (v3.0) for ONE start, written warp-collectively.
+// L-BFGS-B (v3.0) for ONE start -- the algorithm, written once and compiled in three variants.
 //
 // Replaces scipy.optimize.minimize(method="L-BFGS-B", jac=True, bounds=...) as called per
 // start at bore/mixins.py:59-60 and bore/optimizers/base.py:59.  SciPy is a third-party
@@ -9,71 +9,85 @@
 // minimisation with projection, dcsrch line search, limited-memory BFGS update, and the
 // driver loop of scipy/optimize/_lbfgsb_py.py:406-443 (nit / maxiter / maxfun / status).
 //
-// Execution model.  On the device one WARP owns one start: vectors of length n are spread
-// over the 32 lanes (`LB_FOR`), reductions are xor-butterflies (bit-identical on every lane),
-// small dense factorisations run column-parallel with __syncwarp between steps, and scalar
-// control flow is replicated on every lane (warp-uniform).  Compiled for the host
-// (LB_NL == 1) the same code is a plain serial program, which is how it is pinned against
-// SciPy's setulb request by request in tests/ -- the host build is test infrastructure; the
-// product only ever runs the device build.
+// Variants (the includer defines LB_VARIANT; lbfgsb_types.h holds what is common):
+//
+//   LB_VARIANT 1  "warp"    the product: one WARP owns one start, its state staged in shared
+//                 memory.  Vectors of length n are spread over the 32 lanes (LB_FOR),
+//                 reductions are xor-butterflies (bit-identical on every lane), the small
+//                 factorisations run column-parallel, triangular solves keep their vector in
+//                 registers and pass the pivot by shuffle, scalar control flow is replicated
+//                 on every lane (warp-uniform).
+//   LB_VARIANT 0  "host"    the same algorithm as a plain serial program compiled by g++:
+//                 TEST INFRASTRUCTURE, pinned against SciPy's setulb request by request in
+//                 tests/ (the product only ever runs the device variant).  Where the warp
+//                 variant walks an index list, the serial one sweeps all n variables with a
+//                 mask; the sums are the same up to rounding.
 //
 // All algebra is fp64 (SciPy's is); the objective and gradient arrive as fp32 values from
 // the MLP kernel, exactly like the reference's fp32 Keras model feeding fp64 SciPy
 // (bore/decorators.py:54-56).
-#pragma once
-#include <float.h>
-#include <math.h>
+#include "lbfgsb_types.h"
 
-#ifdef __CUDACC__
-#define LB_HD __host__ __device__ inline
-#else
-#define LB_HD inline
+#ifndef LB_VARIANT
+#error "define LB_VARIANT (0 host serial, 1 device warp) before including lbfgsb_core.h"
 #endif
 
-#if defined(__CUDA_ARCH__)
+#undef LB_FN
+#undef LB_WARP
+#undef LB_LANE
+#undef LB_NL
+#undef LB_SYNC
+#undef LB_FOR
+#if LB_VARIANT == 0
+#define LB_FN inline
+#else
+#define LB_FN __device__ inline
+#endif
+#if LB_VARIANT == 1
+#define LB_WARP 1
 #define LB_LANE ((int)(threadIdx.x & 31))
 #define LB_NL 32
 #define LB_SYNC() __syncwarp()
 #else
+#define LB_WARP 0
 #define LB_LANE 0
 #define LB_NL 1
 #define LB_SYNC() ((void)0)
 #endif
-
 #define LB_FOR(i, n) for (int i = LB_LANE; i < (n); i += LB_NL)
-#define LB_MMAX 10
-#define LB_INF (1.0 / 0.0)
-#define LB_EPSMCH DBL_EPSILON
+
+typedef double *LbDP;
+typedef int *LbIP;
 
 // ------------------------------------------------------------------ warp collectives
-LB_HD double lb_sum(double v) {
-#if defined(__CUDA_ARCH__)
+LB_FN double lb_sum(double v) {
+#if LB_WARP
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
 #endif
   return v;
 }
-LB_HD double lb_max(double v) {
-#if defined(__CUDA_ARCH__)
+LB_FN double lb_max(double v) {
+#if LB_WARP
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
 #endif
   return v;
 }
-LB_HD int lb_isum(int v) {
-#if defined(__CUDA_ARCH__)
+LB_FN int lb_isum(int v) {
+#if LB_WARP
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
 #endif
   return v;
 }
-LB_HD int lb_any(int p) {
-#if defined(__CUDA_ARCH__)
+LB_FN int lb_any(int p) {
+#if LB_WARP
   return __any_sync(0xffffffffu, p);
 #else
   return p;
 #endif
 }
 // minimum value and the SMALLEST index attaining it
-LB_HD void lb_argmin(double &v, int &idx) {
-#if defined(__CUDA_ARCH__)
+LB_FN void lb_argmin(double &v, int &idx) {
+#if LB_WARP
   for (int o = 16; o > 0; o >>= 1) {
     double ov = __shfl_xor_sync(0xffffffffu, v, o);
     int oi = __shfl_xor_sync(0xffffffffu, idx, o);
@@ -82,155 +96,196 @@ LB_HD void lb_argmin(double &v, int &idx) {
 #endif
 }
 
-// ------------------------------------------------------------------ problem + state
-struct LbParams {
-  int n, m;
-  int maxiter, maxfun, maxls;
-  int cnstnd, boxed;  // any bounded variable / all variables boxed
-  double ftol;        // factr * epsmch
-  double pgtol;
-  const double *lo, *hi;  // [n]
-  const int *nbd;         // [n] 0 none, 1 lower, 2 both, 3 upper
-};
-
-enum { LB_PH_START = 0, LB_PH_LNSRCH = 1, LB_PH_DONE = 2 };
-enum { LB_LS_START = 0, LB_LS_FG = 1, LB_LS_CONV = 2, LB_LS_WARN = 3, LB_LS_ERROR = 4 };
-
-// persisted per start between evaluation rounds
-struct LbScal {
-  double f, fold, theta, gd, gdold, dtd, dnorm, stp, stpmx, sbgnrm;
-  // dcsrch
-  double finit, ginit, gtest, gx, gy, fx, fy, stx, sty, stmin, stmax, width, width1;
-  int phase, col, iupdat, iter, nit, nfev, ifun, iback, updatd, status, task;
-  int brackt, stage, ls_task, nskip, nintol;
-};
-
-#define LB_LDW(m) (2 * (m) + 1)
-
 // scratch + state views for one start (all in fast memory while a step runs)
+//
+// Limited-memory matrices.  W = [Y S] holds the correction pairs; SY = S'Y, SS = S'S and
+// YY = Y'Y are kept as FULL m x m matrices (the original keeps the lower triangle of SY and the
+// upper triangle of SS only): with the totals at hand, a sum over the free variables is
+// total - sum over the active ones, so formk only ever walks the SMALLER of the two index sets.
+// The middle-matrix product of bmv is applied through precomputed operators instead of two
+// triangular solves per call: tinv = T^-1 (T = theta*SS + L D^-1 L', formt) and
+// ld = L D^-1 (strictly lower) with 1/D on its diagonal, so that
+//   p2 = tinv (v2 + ld v1),   p1 = -D^-1 v1 + ld' p2
+// is three short matrix-vector products with no serial chain.
 struct LbWork {
-  double *x, *g, *z, *r, *d, *t, *xp;  // [n]
-  double *W;                          // [n][LDW]: wy cols 0..m-1, ws cols m..2m-1 (logical order)
-  double *sy, *ss, *wt;               // [m][m]
-  double *wn;                         // [2m][2m] upper triangle
-  double *p, *c, *wbp, *v;            // [2m]
-  int *iwhere;                        // [n]
-  int *index;                         // [n] free variables first (count nfree), active after
+  LbDP x, g, z, r, d, t, xp;          // [n]
+  LbDP W;                             // [n][LDW]: wy cols 0..m-1, ws cols m..2m-1 (logical order)
+  LbDP sy, ss, yy, tinv;              // [m][m] persisted (contiguous, in this order)
+  double *ld;                         // [m][m] derived from sy (lb_prep_ld)
+  double *wn;                         // [2m][2m] upper triangle (also scratch of formt)
+  double *rd;                         // [2m] reciprocal diagonal of the last Cholesky factors
+  double *p, *c, *wbp, *v, *q;        // [2m]
+  LbIP iwhere;                        // [n]
+  LbIP index;                         // [n] free variables first (count nfree), active after
+                                      //     (warp variant only; the serial variants mask)
 };
 
 LB_HD size_t lb_work_doubles(int n, int m) {
-  return (size_t)7 * n + (size_t)n * LB_LDW(m) + 3 * m * m + 4 * m * m + 8 * m;
+  return (size_t)7 * n + (size_t)n * LB_LDW(m) + 5 * m * m + 4 * m * m + 12 * m;
 }
 LB_HD size_t lb_work_ints(int n) { return 2 * (size_t)n; }
 
-LB_HD void lb_carve(LbWork &w, double *dbase, int *ibase, int n, int m) {
+LB_FN void lb_carve(LbWork &w, double *dbase, int *ibase, int n, int m) {
   double *q = dbase;
   w.x = q; q += n; w.g = q; q += n; w.z = q; q += n; w.r = q; q += n;
   w.d = q; q += n; w.t = q; q += n; w.xp = q; q += n;
   w.W = q; q += (size_t)n * LB_LDW(m);
-  w.sy = q; q += m * m; w.ss = q; q += m * m; w.wt = q; q += m * m;
+  w.sy = q; q += m * m; w.ss = q; q += m * m; w.yy = q; q += m * m; w.tinv = q; q += m * m;
+  w.ld = q; q += m * m;
   w.wn = q; q += 4 * m * m;
+  w.rd = q; q += 2 * m;
   w.p = q; q += 2 * m; w.c = q; q += 2 * m; w.wbp = q; q += 2 * m; w.v = q; q += 2 * m;
+  w.q = q; q += 2 * m;
   w.iwhere = ibase; w.index = ibase + n;
 }
 
 // ------------------------------------------------------------------ small dense kernels
-// Cholesky A = R'R in place, R in the upper triangle (LINPACK dpofa).  0 ok, else k+1.
-LB_HD int lb_chol(double *A, int ld, int n) {
+// Cholesky A = R'R in place, R in the upper triangle (LINPACK dpofa); rd[k] = 1/R[k][k].
+// 0 ok, else k+1.  Right-looking: after column k is scaled, lane j owns column k+1+j of the
+// trailing block and walks its rows, so there is no index arithmetic in the inner loop.
+LB_FN int lb_chol(double *A, int ld, int n, double *rd) {
   for (int k = 0; k < n; ++k) {
     LB_SYNC();
     const double akk = A[k * ld + k];
     if (!(akk > 0.0)) return k + 1;
     const double rkk = sqrt(akk);
-    for (int j = k + 1 + LB_LANE; j < n; j += LB_NL) A[k * ld + j] /= rkk;
+#if LB_WARP
+    const double rinv = rsqrt(akk);  // independent of the sqrt: both issue back to back
+#else
+    const double rinv = 1.0 / rkk;
+#endif
+    for (int j = k + 1 + LB_LANE; j < n; j += LB_NL) A[k * ld + j] *= rinv;
     LB_SYNC();
-    if (LB_LANE == 0) A[k * ld + k] = rkk;
-    const int r = n - k - 1;  // trailing block, pairs (i<=j) in k+1..n-1
-    for (int e = LB_LANE; e < r * r; e += LB_NL) {
-      const int i = k + 1 + e / r, j = k + 1 + e % r;
-      if (i <= j) A[i * ld + j] -= A[k * ld + i] * A[k * ld + j];
+    if (LB_LANE == 0) { A[k * ld + k] = rkk; rd[k] = rinv; }
+    for (int j = k + 1 + LB_LANE; j < n; j += LB_NL) {
+      const double akj = A[k * ld + j];
+      for (int i = k + 1; i <= j; ++i) A[i * ld + j] -= A[k * ld + i] * akj;
     }
   }
   LB_SYNC();
   return 0;
 }
 
-// solve R' x = b, R upper (dtrsl job 11); b overwritten
-LB_HD int lb_trsl_t(const double *R, int ld, int n, double *b) {
-  for (int k = 0; k < n; ++k)
-    if (R[k * ld + k] == 0.0) return k + 1;
-  double xprev = 0.0;
+// solve R' x = b (R upper; dtrsl job 11), b overwritten; n <= 32 on the device, where lane i
+// keeps b[i] in a register and the pivot travels by shuffle (no shared-memory round trip in
+// the serial chain).  rd = reciprocal diagonal from lb_chol.
+LB_FN void lb_trsl_t(const double *R, int ld, int n, const double *rd, double *b) {
+  LB_SYNC();
+#if LB_WARP
+  const int i = LB_LANE;
+  double bi = i < n ? b[i] : 0.0;
   for (int k = 0; k < n; ++k) {
-    LB_SYNC();
-    if (k > 0 && LB_LANE == 0) b[k - 1] = xprev;
-    const double xk = b[k] / R[k * ld + k];
-    for (int i = k + 1 + LB_LANE; i < n; i += LB_NL) b[i] -= R[k * ld + i] * xk;
-    xprev = xk;
+    const double rki = (i > k && i < n) ? R[k * ld + i] : 0.0;
+    const double xk = __shfl_sync(0xffffffffu, bi, k) * rd[k];
+    if (i == k) bi = xk;
+    bi -= rki * xk;
   }
+  if (i < n) b[i] = bi;
+#else
+  for (int k = 0; k < n; ++k) {
+    const double xk = b[k] * rd[k];
+    b[k] = xk;
+    for (int i = k + 1; i < n; ++i) b[i] -= R[k * ld + i] * xk;
+  }
+#endif
   LB_SYNC();
-  if (n > 0 && LB_LANE == 0) b[n - 1] = xprev;
-  LB_SYNC();
-  return 0;
 }
 
-// solve R x = b, R upper (dtrsl job 01); b overwritten
-LB_HD int lb_trsl_n(const double *R, int ld, int n, double *b) {
-  for (int k = 0; k < n; ++k)
-    if (R[k * ld + k] == 0.0) return k + 1;
-  double xprev = 0.0;
+// solve R x = b (R upper; dtrsl job 01), b overwritten
+LB_FN void lb_trsl_n(const double *R, int ld, int n, const double *rd, double *b) {
+  LB_SYNC();
+#if LB_WARP
+  const int i = LB_LANE;
+  double bi = i < n ? b[i] : 0.0;
   for (int k = n - 1; k >= 0; --k) {
-    LB_SYNC();
-    if (k < n - 1 && LB_LANE == 0) b[k + 1] = xprev;
-    const double xk = b[k] / R[k * ld + k];
-    for (int i = LB_LANE; i < k; i += LB_NL) b[i] -= R[i * ld + k] * xk;
-    xprev = xk;
+    const double rik = i < k ? R[i * ld + k] : 0.0;
+    const double xk = __shfl_sync(0xffffffffu, bi, k) * rd[k];
+    if (i == k) bi = xk;
+    bi -= rik * xk;
   }
+  if (i < n) b[i] = bi;
+#else
+  for (int k = n - 1; k >= 0; --k) {
+    const double xk = b[k] * rd[k];
+    b[k] = xk;
+    for (int i = 0; i < k; ++i) b[i] -= R[i * ld + k] * xk;
+  }
+#endif
   LB_SYNC();
-  if (n > 0 && LB_LANE == 0) b[0] = xprev;
-  LB_SYNC();
-  return 0;
 }
 
-// p = M v with M the 2col x 2col middle matrix of the compact L-BFGS formula (bmv)
-LB_HD int lb_bmv(const double *sy, const double *wt, int m, int col, const double *v, double *p) {
-  if (col == 0) return 0;
+// ld = L D^-1 below the diagonal, 1/D on it (L, D = strictly lower part / diagonal of SY)
+LB_FN void lb_prep_ld(LbWork &w, int m, int col) {
   LB_SYNC();
-  LB_FOR(i, col) {
-    double s = 0.0;
-    for (int k = 0; k < i; ++k) s += sy[i * m + k] * v[k] / sy[k * m + k];
-    p[col + i] = v[col + i] + s;
-    p[i] = v[i] / sqrt(sy[i * m + i]);
-  }
-  int info = lb_trsl_t(wt, m, col, p + col);
-  if (info) return info;
-  info = lb_trsl_n(wt, m, col, p + col);
-  if (info) return info;
-  LB_FOR(i, col) {
-    double pi = -p[i] / sqrt(sy[i * m + i]);
-    double s = 0.0;
-    for (int k = i + 1; k < col; ++k) s += sy[k * m + i] * p[col + k] / sy[i * m + i];
-    p[i] = pi + s;
-  }
+  LB_FOR(k, col) w.ld[k * m + k] = 1.0 / w.sy[k * m + k];
   LB_SYNC();
-  return 0;
+  for (int i = 1; i < col; ++i)
+    for (int k = LB_LANE; k < i; k += LB_NL) w.ld[i * m + k] = w.sy[i * m + k] * w.ld[k * m + k];
+  LB_SYNC();
 }
 
-// T = theta*SS + L D^-1 L' (upper), then Cholesky into wt (formt)
-LB_HD int lb_formt(double *wt, const double *sy, const double *ss, int m, int col, double theta) {
+// p = M v with M the inverse 2col x 2col middle matrix of the compact L-BFGS formula (bmv),
+// through the precomputed operators tinv and ld (see LbWork).  v and p must not alias.
+LB_FN void lb_bmv(const LbWork &w, int m, int col, const double *v, double *p) {
+  if (col == 0) return;
   LB_SYNC();
-  for (int e = LB_LANE; e < col * col; e += LB_NL) {
-    const int i = e / col, j = e % col;
-    if (i > j) continue;
-    double s = 0.0;
-    for (int k = 0; k < i; ++k) s += sy[i * m + k] * sy[j * m + k] / sy[k * m + k];
-    wt[i * m + j] = s + theta * ss[i * m + j];
+  LB_FOR(i, col) {
+    double a = v[col + i];
+    for (int k = 0; k < i; ++k) a += w.ld[i * m + k] * v[k];
+    w.q[i] = a;
   }
-  const int info = lb_chol(wt, m, col);
-  return info ? -3 : 0;
+  LB_SYNC();
+  LB_FOR(i, col) {
+    double a = 0.0;
+    for (int j = 0; j < col; ++j) a += w.tinv[i * m + j] * w.q[j];
+    p[col + i] = a;
+  }
+  LB_SYNC();
+  LB_FOR(i, col) {
+    double a = -w.ld[i * m + i] * v[i];
+    for (int k = i + 1; k < col; ++k) a += w.ld[k * m + i] * p[col + k];
+    p[i] = a;
+  }
+  LB_SYNC();
+}
+
+// T = theta*SS + L D^-1 L' (formt), Cholesky-factored in scratch (w.wn), then inverted into
+// w.tinv: every later bmv is a plain matrix-vector product.  Returns nonzero when T is not
+// positive definite (the caller refreshes the memory, like the original).
+LB_FN int lb_formt(LbWork &w, int m, int col, double theta) {
+  double *T = w.wn;             // [col][m] upper triangle -> R
+  double *Ri = w.wn + m * m;    // [col][m] upper triangle: R^-1
+  lb_prep_ld(w, m, col);
+  for (int i = 0; i < col; ++i)
+    for (int j = i + LB_LANE; j < col; j += LB_NL) {
+      double a = theta * w.ss[i * m + j];
+      for (int k = 0; k < i; ++k) a += w.ld[i * m + k] * w.sy[j * m + k];
+      T[i * m + j] = a;
+    }
+  if (lb_chol(T, m, col, w.rd)) return -3;
+  // R^-1 column by column (lane j solves R x = e_j by back substitution; rows > j are zero)
+  LB_FOR(j, col) {
+    for (int k = j; k >= 0; --k) {
+      double a = k == j ? 1.0 : 0.0;
+      for (int i = k + 1; i <= j; ++i) a -= T[k * m + i] * Ri[i * m + j];
+      Ri[k * m + j] = a * w.rd[k];
+    }
+  }
+  LB_SYNC();
+  // T^-1 = R^-1 R^-T (symmetric, stored full)
+  for (int i = 0; i < col; ++i)
+    for (int j = i + LB_LANE; j < col; j += LB_NL) {
+      double a = 0.0;
+      for (int k = j; k < col; ++k) a += Ri[i * m + k] * Ri[j * m + k];
+      w.tinv[i * m + j] = a;
+      w.tinv[j * m + i] = a;
+    }
+  LB_SYNC();
+  return 0;
 }
 
 // ------------------------------------------------------------------ projected gradient norm
-LB_HD double lb_projgr(const LbParams &P, const double *x, const double *g) {
+LB_FN double lb_projgr(const LbParams &P, const LbDP x, const LbDP g) {
   double s = 0.0;
   LB_FOR(i, P.n) {
     double gi = g[i];
@@ -251,10 +306,10 @@ LB_HD double lb_projgr(const LbParams &P, const double *x, const double *g) {
 // Breakpoints live in w.t (free until the line search starts), the Cauchy direction in w.d,
 // the Cauchy point in w.z; w.c receives W'(xcp - x).  Instead of the heap of the original
 // (hpsolb) the next breakpoint is a warp arg-min over the remaining ones.
-LB_HD int lb_cauchy(const LbParams &P, LbWork &w, const LbScal &s, int &nseg_out) {
+LB_FN int lb_cauchy(const LbParams &P, LbWork &w, const LbScal &s, int &nseg_out) {
   const int n = P.n, m = P.m, col = s.col, col2 = 2 * col, ldw = LB_LDW(m);
   const double theta = s.theta;
-  double *tb = w.t, *d = w.d, *xcp = w.z;
+  LbDP tb = w.t, d = w.d, xcp = w.z;
   nseg_out = 0;
   LB_SYNC();
   if (s.sbgnrm <= 0.0) {
@@ -300,7 +355,7 @@ LB_HD int lb_cauchy(const LbParams &P, LbWork &w, const LbScal &s, int &nseg_out
   LB_SYNC();
   // p = W'd (ws half scaled by theta), c = 0
   for (int j = LB_LANE; j < col2; j += LB_NL) {
-    const double *wc = w.W + (j < col ? j : m + (j - col));
+    const LbDP wc = w.W + (j < col ? j : m + (j - col));
     double a = 0.0;
     for (int i = 0; i < n; ++i) a += wc[i * ldw] * d[i];
     w.p[j] = j < col ? a : theta * a;
@@ -312,8 +367,7 @@ LB_HD int lb_cauchy(const LbParams &P, LbWork &w, const LbScal &s, int &nseg_out
   double f2 = -theta * f1;
   const double f2_org = f2;
   if (col > 0) {
-    const int info = lb_bmv(w.sy, w.wt, m, col, w.p, w.v);
-    if (info) return info;
+    lb_bmv(w, m, col, w.p, w.v);
     double a = 0.0;
     for (int j = LB_LANE; j < col2; j += LB_NL) a += w.v[j] * w.p[j];
     f2 -= lb_sum(a);
@@ -363,8 +417,7 @@ LB_HD int lb_cauchy(const LbParams &P, LbWork &w, const LbScal &s, int &nseg_out
           w.c[j] += dt * w.p[j];
           w.wbp[j] = j < col ? w.W[ibp * ldw + j] : theta * w.W[ibp * ldw + m + (j - col)];
         }
-        const int info = lb_bmv(w.sy, w.wt, m, col, w.wbp, w.v);
-        if (info) return info;
+        lb_bmv(w, m, col, w.wbp, w.v);
         double wmc = 0.0, wmp = 0.0, wmw = 0.0;
         for (int j = LB_LANE; j < col2; j += LB_NL) {
           const double vj = w.v[j];
@@ -399,10 +452,10 @@ LB_HD int lb_cauchy(const LbParams &P, LbWork &w, const LbScal &s, int &nseg_out
 
 // ------------------------------------------------------------------ free / active sets at the GCP
 // index[0..nfree) = free variables (iwhere <= 0) in ascending order, the rest active.
-LB_HD int lb_freev(const LbParams &P, LbWork &w) {
+LB_FN int lb_freev(const LbParams &P, LbWork &w) {
   const int n = P.n;
   LB_SYNC();
-#if defined(__CUDA_ARCH__)
+#if LB_WARP
   int base_f = 0, base_a = 0;
   // ordered compaction, 32 variables at a time
   int nfree_total = 0;
@@ -426,94 +479,205 @@ LB_HD int lb_freev(const LbParams &P, LbWork &w) {
   LB_SYNC();
   return nfree_total;
 #else
+  // serial variants sweep all n variables with the iwhere mask instead of an index list
   int nfree = 0;
-  for (int i = 0; i < n; ++i) if (w.iwhere[i] <= 0) w.index[nfree++] = i;
-  int na = nfree;
-  for (int i = 0; i < n; ++i) if (w.iwhere[i] > 0) w.index[na++] = i;
+  for (int i = 0; i < n; ++i) nfree += (w.iwhere[i] <= 0);
   return nfree;
 #endif
 }
 
 // ------------------------------------------------------------------ K = LEL' factorisation (formk)
 // Built from scratch each time it is needed (the original updates it incrementally; the
-// matrix is the same).  wn: upper triangle of the 2col x 2col matrix, leading dim 2m.
-LB_HD int lb_formk(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
+// matrix is the same).  wn: upper triangle of the 2col x 2col matrix, leading dim 2m:
+//   (1,1)  Y'ZZ'Y / theta + D        Z = free variables, A = active variables
+//   (2,2)  theta * S'AA'S
+//   (1,2)  R_z (s_i' Z Z' y_j, j >= i)  and  -L_a (s_i' A A' y_j, j < i)
+// The three Gram sums  Gyy = Y_Q'Y_Q, Gss = S_Q'S_Q, Gsy = S_Q'Y_Q  are taken over ONE index
+// set Q, the smaller of Z and A; the sums over the other set are  total - G  with the totals
+// YY, SS, SY kept up to date by matupd.  Output o of the 2*tri+col^2 sums is owned by lane
+// o % 32, which keeps it in a register while the warp walks the rows of Q.
+#define LB_FORMK_ACC 7  // ceil((2*55 + 100) / 32) for m = 10
+LB_FN void lb_formk_decode(int o, int col, int m, int &type, int &i, int &j, int &ca, int &cb) {
+  const int ntri = col * (col + 1) / 2;
+  if (o < 2 * ntri) {
+    type = o >= ntri;
+    int q = type ? o - ntri : o;
+    // q = i*(i+1)/2 + j, i >= j: closed-form unranking, corrected for rounding
+    i = (int)((sqrtf(8.f * (float)q + 1.f) - 1.f) * 0.5f);
+    if ((i + 1) * (i + 2) / 2 <= q) ++i;
+    if (i * (i + 1) / 2 > q) --i;
+    j = q - i * (i + 1) / 2;
+    ca = type ? m + i : i;
+    cb = type ? m + j : j;
+  } else {
+    type = 2;
+    const int q = o - 2 * ntri;
+    i = q / col;  // s index
+    j = q - i * col;  // y index
+    ca = m + i;
+    cb = j;
+  }
+}
+
+#if !LB_WARP
+// Serial Gram sweeps over the FREE variables (iwhere <= 0), one output family per sweep so
+// that the accumulators live in registers: every loop below has compile-time bounds and the
+// columns >= col contribute zeros.
+//   lb_gram_sym : sum_i v_a(i) v_b(i), a >= b, for the column block starting at `coff`
+//   lb_gram_sy  : sum_i s_a(i) y_b(i) for a in [A0, A0 + LB_MMAX/2)
+LB_FN void lb_gram_sym(const LbParams &P, const LbWork &w, int col, int coff, double *out) {
+  const int n = P.n, ldw = LB_LDW(P.m);
+  double acc[LB_MMAX * (LB_MMAX + 1) / 2];
+#pragma unroll
+  for (int e = 0; e < LB_MMAX * (LB_MMAX + 1) / 2; ++e) acc[e] = 0.0;
+  for (int i = 0; i < n; ++i) {
+    if (w.iwhere[i] > 0) continue;
+    const LbDP row = w.W + (i * ldw + coff);
+    double v[LB_MMAX];
+#pragma unroll
+    for (int a = 0; a < LB_MMAX; ++a) v[a] = a < col ? row[a] : 0.0;
+#pragma unroll
+    for (int a = 0; a < LB_MMAX; ++a)
+#pragma unroll
+      for (int b = 0; b <= a; ++b) acc[a * (a + 1) / 2 + b] += v[a] * v[b];
+  }
+#pragma unroll
+  for (int e = 0; e < LB_MMAX * (LB_MMAX + 1) / 2; ++e) out[e] = acc[e];
+}
+template <int A0>
+LB_FN void lb_gram_sy(const LbParams &P, const LbWork &w, int col, double *out) {
+  const int n = P.n, m = P.m, ldw = LB_LDW(P.m);
+  constexpr int NA = LB_MMAX / 2;
+  double acc[NA * LB_MMAX];
+#pragma unroll
+  for (int e = 0; e < NA * LB_MMAX; ++e) acc[e] = 0.0;
+  for (int i = 0; i < n; ++i) {
+    if (w.iwhere[i] > 0) continue;
+    const LbDP row = w.W + i * ldw;
+    double sv[NA], yv[LB_MMAX];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) sv[a] = A0 + a < col ? row[m + A0 + a] : 0.0;
+#pragma unroll
+    for (int b = 0; b < LB_MMAX; ++b) yv[b] = b < col ? row[b] : 0.0;
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+      for (int b = 0; b < LB_MMAX; ++b) acc[a * LB_MMAX + b] += sv[a] * yv[b];
+  }
+#pragma unroll
+  for (int e = 0; e < NA * LB_MMAX; ++e) out[(A0 + e / LB_MMAX) * LB_MMAX + e % LB_MMAX] = acc[e];
+}
+#endif
+
+LB_FN int lb_formk(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
   const int n = P.n, m = P.m, col = s.col, ldw = LB_LDW(m), ldn = 2 * m;
   const double theta = s.theta;
-  const double *W = w.W;
-  const int *ind = w.index;
   LB_SYNC();
+#if LB_WARP
+  const LbDP W = w.W;
+  const bool over_free = nfree <= n - nfree;
+  const LbIP ind = over_free ? w.index : w.index + nfree;
+  const int nq = over_free ? nfree : n - nfree;
   const int ntri = col * (col + 1) / 2;
-  const int ntask = 2 * ntri + col * col;
-  for (int e = LB_LANE; e < ntask; e += LB_NL) {
-    if (e < 2 * ntri) {
-      const bool second = e >= ntri;
-      int q = second ? e - ntri : e;
-      // unrank (iy >= jy) from q = iy*(iy+1)/2 + jy
-      int iy = 0;
-      while ((iy + 1) * (iy + 2) / 2 <= q) ++iy;
-      const int jy = q - iy * (iy + 1) / 2;
-      double a = 0.0;
-      if (!second) {  // Y'ZZ'Y over free variables
-        for (int k = 0; k < nfree; ++k) {
-          const double *row = W + ind[k] * ldw;
-          a += row[iy] * row[jy];
-        }
-        a /= theta;
-        if (iy == jy) a += w.sy[iy * m + iy];
-        w.wn[jy * ldn + iy] = a;
-      } else {  // S'AA'S over active variables
-        for (int k = nfree; k < n; ++k) {
-          const double *row = W + ind[k] * ldw + m;
-          a += row[iy] * row[jy];
-        }
-        w.wn[(col + jy) * ldn + (col + iy)] = a * theta;
-      }
-    } else {
-      const int q = e - 2 * ntri;
-      const int iy = q / col, jy = q % col;  // ws column iy with wy column jy
-      double a = 0.0;
-      if (jy >= iy) {  // R_z: free variables
-        for (int k = 0; k < nfree; ++k) {
-          const double *row = W + ind[k] * ldw;
-          a += row[m + iy] * row[jy];
-        }
-        w.wn[jy * ldn + (col + iy)] = a;
-      } else {  // L_a: active variables, negated
-        for (int k = nfree; k < n; ++k) {
-          const double *row = W + ind[k] * ldw;
-          a += row[m + iy] * row[jy];
-        }
-        w.wn[jy * ldn + (col + iy)] = -a;
-      }
+  const int nout = 2 * ntri + col * col;
+  double acc[LB_FORMK_ACC];
+  int code[LB_FORMK_ACC];  // ty | i << 2 | j << 8 | ca << 14 | cb << 22
+#pragma unroll
+  for (int t = 0; t < LB_FORMK_ACC; ++t) {
+    int ty = 0, i = 0, j = 0, ca = 0, cb = 0;
+    const int o = LB_LANE + 32 * t;
+    acc[t] = 0.0;
+    if (o < nout) lb_formk_decode(o, col, m, ty, i, j, ca, cb);
+    code[t] = ty | i << 2 | j << 8 | ca << 14 | cb << 22;
+  }
+  for (int k = 0; k < nq; ++k) {
+    const LbDP row = W + ind[k] * ldw;
+#pragma unroll
+    for (int t = 0; t < LB_FORMK_ACC; ++t)
+      acc[t] += row[(code[t] >> 14) & 255] * row[(code[t] >> 22) & 255];
+  }
+#pragma unroll
+  for (int t = 0; t < LB_FORMK_ACC; ++t) {
+    const int o = LB_LANE + 32 * t;
+    if (o >= nout) continue;
+    const int ty = code[t] & 3, i = (code[t] >> 2) & 63, j = (code[t] >> 8) & 63;
+    const double g = acc[t];
+    if (ty == 0) {         // Y'ZZ'Y/theta + D at (j, i), i >= j
+      double a = over_free ? g : w.yy[i * m + j] - g;
+      a /= theta;
+      if (i == j) a += w.sy[i * m + i];
+      w.wn[j * ldn + i] = a;
+    } else if (ty == 1) {  // theta * S'AA'S at (col+j, col+i), i >= j
+      const double a = over_free ? w.ss[i * m + j] - g : g;
+      w.wn[(col + j) * ldn + (col + i)] = a * theta;
+    } else {               // ws column i with wy column j, at (j, col+i)
+      if (j >= i) w.wn[j * ldn + (col + i)] = over_free ? g : w.sy[i * m + j] - g;
+      else w.wn[j * ldn + (col + i)] = -(over_free ? w.sy[i * m + j] - g : g);
     }
   }
+#else
+  (void)nfree; (void)n; (void)ldw;
+  {
+    double G[LB_MMAX * LB_MMAX];  // one family at a time
+    lb_gram_sym(P, w, col, 0, G);  // Y'ZZ'Y
+    for (int i = 0; i < col; ++i)
+      for (int j = 0; j <= i; ++j) {
+        double a = G[i * (i + 1) / 2 + j] / theta;
+        if (i == j) a += w.sy[i * m + i];
+        w.wn[j * ldn + i] = a;
+      }
+    lb_gram_sym(P, w, col, m, G);  // S'ZZ'S; the active part is the total minus it
+    for (int i = 0; i < col; ++i)
+      for (int j = 0; j <= i; ++j)
+        w.wn[(col + j) * ldn + (col + i)] = (w.ss[i * m + j] - G[i * (i + 1) / 2 + j]) * theta;
+    lb_gram_sy<0>(P, w, col, G);   // S'ZZ'Y, s index i, y index j
+    lb_gram_sy<LB_MMAX / 2>(P, w, col, G);
+    for (int i = 0; i < col; ++i)
+      for (int j = 0; j < col; ++j) {
+        const double g = G[i * LB_MMAX + j];
+        w.wn[j * ldn + (col + i)] = j >= i ? g : -(w.sy[i * m + j] - g);
+      }
+  }
+#endif
   // Cholesky of the (1,1) block
-  if (lb_chol(w.wn, ldn, col)) return -1;
-  // (1,2) block: L^-1 (-L_a' + R_z'), one right-hand side per lane
-  for (int js = col + LB_LANE; js < 2 * col; js += LB_NL) {
+  if (lb_chol(w.wn, ldn, col, w.rd)) return -1;
+  // (1,2) block := L11^-1 (1,2): right-looking forward elimination over all col right-hand
+  // sides at once (lane -> (row offset, rhs) fixed outside the loop)
+  {
+    const int js = col + LB_LANE % col, isub = LB_LANE / col;
+    const int nsub = LB_NL >= col ? LB_NL / col : 1;
     for (int k = 0; k < col; ++k) {
-      double b = w.wn[k * ldn + js];
-      for (int i = 0; i < k; ++i) b -= w.wn[i * ldn + k] * w.wn[i * ldn + js];
-      w.wn[k * ldn + js] = b / w.wn[k * ldn + k];
+      for (int c = col + LB_LANE; c < 2 * col; c += LB_NL) w.wn[k * ldn + c] *= w.rd[k];
+      LB_SYNC();
+#if LB_WARP
+      if (isub < nsub) {
+        const double xk = w.wn[k * ldn + js];
+        for (int i = k + 1 + isub; i < col; i += nsub) w.wn[i * ldn + js] -= w.wn[k * ldn + i] * xk;
+      }
+#else
+      for (int c = col; c < 2 * col; ++c) {
+        const double xk = w.wn[k * ldn + c];
+        for (int i = k + 1; i < col; ++i) w.wn[i * ldn + c] -= w.wn[k * ldn + i] * xk;
+      }
+      (void)js; (void)isub; (void)nsub;
+#endif
+      LB_SYNC();
     }
   }
-  LB_SYNC();
   // (2,2) block += (1,2)'(1,2), upper triangle
-  for (int e = LB_LANE; e < col * col; e += LB_NL) {
-    const int is = col + e / col, js = col + e % col;
-    if (is > js) continue;
-    double a = 0.0;
-    for (int k = 0; k < col; ++k) a += w.wn[k * ldn + is] * w.wn[k * ldn + js];
-    w.wn[is * ldn + js] += a;
-  }
-  if (lb_chol(w.wn + col * ldn + col, ldn, col)) return -2;
+  for (int is = col; is < 2 * col; ++is)
+    for (int js = is + LB_LANE; js < 2 * col; js += LB_NL) {
+      double a = 0.0;
+      for (int k = 0; k < col; ++k) a += w.wn[k * ldn + is] * w.wn[k * ldn + js];
+      w.wn[is * ldn + js] += a;
+    }
+  if (lb_chol(w.wn + col * ldn + col, ldn, col, w.rd + col)) return -2;
   return 0;
 }
 
 // ------------------------------------------------------------------ reduced gradient (cmprlb)
 // r[k] = -(B(xcp - x) + g)[k] for free k (0 elsewhere); uses c = W'(xcp - x) from cauchy.
-LB_HD int lb_cmprlb(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
+LB_FN int lb_cmprlb(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
   const int n = P.n, m = P.m, col = s.col, ldw = LB_LDW(m);
   const double theta = s.theta;
   LB_SYNC();
@@ -522,12 +686,11 @@ LB_HD int lb_cmprlb(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
     LB_SYNC();
     return 0;
   }
-  const int info = lb_bmv(w.sy, w.wt, m, col, w.c, w.p);
-  if (info) return -8;
+  lb_bmv(w, m, col, w.c, w.p);
   LB_FOR(i, n) {
     if (w.iwhere[i] <= 0) {
       double a = -theta * (w.z[i] - w.x[i]) - w.g[i];
-      const double *row = w.W + i * ldw;
+      const LbDP row = w.W + i * ldw;
       for (int j = 0; j < col; ++j) a += row[j] * w.p[j] + row[m + j] * (theta * w.p[col + j]);
       w.r[i] = a;
     } else {
@@ -541,25 +704,44 @@ LB_HD int lb_cmprlb(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
 
 // ------------------------------------------------------------------ subspace minimisation (subsm, v3.0)
 // In: w.z = Cauchy point, w.r = reduced gradient.  Out: w.z = subspace minimiser.
-LB_HD int lb_subsm(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
+LB_FN int lb_subsm(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
   const int n = P.n, m = P.m, col = s.col, col2 = 2 * col, ldw = LB_LDW(m), ldn = 2 * m;
   const double theta = s.theta;
   if (nfree <= 0) return 0;
   double *wv = w.v;
   LB_SYNC();
   // wv = W'Z d
+#if LB_WARP
   for (int j = LB_LANE; j < col2; j += LB_NL) {
-    const double *wc = w.W + (j < col ? j : m + (j - col));
+    const LbDP wc = w.W + (j < col ? j : m + (j - col));
     double a = 0.0;
     for (int k = 0; k < nfree; ++k) { const int i = w.index[k]; a += wc[i * ldw] * w.r[i]; }
     wv[j] = j < col ? a : theta * a;
   }
-  // wv := K^-1 wv
-  int info = lb_trsl_t(w.wn, ldn, col2, wv);
-  if (info) return info;
+#else
+  {
+    double acc[2 * LB_MMAX];
+#pragma unroll
+    for (int a = 0; a < 2 * LB_MMAX; ++a) acc[a] = 0.0;
+    for (int i = 0; i < n; ++i) {
+      if (w.iwhere[i] > 0) continue;
+      const double ri = w.r[i];
+      const LbDP row = w.W + i * ldw;
+#pragma unroll
+      for (int a = 0; a < LB_MMAX; ++a)
+        if (a < col) { acc[a] += row[a] * ri; acc[LB_MMAX + a] += row[m + a] * ri; }
+    }
+#pragma unroll
+    for (int a = 0; a < LB_MMAX; ++a)
+      if (a < col) { wv[a] = acc[a]; wv[col + a] = theta * acc[LB_MMAX + a]; }
+  }
+#endif
+  // wv := K^-1 wv  (the first col entries are pre-divided by theta for the loop below)
+  lb_trsl_t(w.wn, ldn, col2, w.rd, wv);
   for (int j = LB_LANE; j < col; j += LB_NL) wv[j] = -wv[j];
-  info = lb_trsl_n(w.wn, ldn, col2, wv);
-  if (info) return info;
+  lb_trsl_n(w.wn, ldn, col2, w.rd, wv);
+  for (int j = LB_LANE; j < col; j += LB_NL) wv[j] /= theta;
+  LB_SYNC();
   // d = (1/theta) d + (1/theta^2) Z'W wv ; xp = xcp ; projected Newton point
   int iword = 0;
   LB_FOR(i, n) {
@@ -567,8 +749,8 @@ LB_HD int lb_subsm(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
     w.xp[i] = zi;
     if (w.iwhere[i] <= 0) {
       double dk = w.r[i];
-      const double *row = w.W + i * ldw;
-      for (int j = 0; j < col; ++j) dk += row[j] * wv[j] / theta + row[m + j] * wv[col + j];
+      const LbDP row = w.W + i * ldw;
+      for (int j = 0; j < col; ++j) dk += row[j] * wv[j] + row[m + j] * wv[col + j];
       dk *= 1.0 / theta;
       w.r[i] = dk;
       const int nb = P.nbd[i];
@@ -638,169 +820,38 @@ LB_HD int lb_subsm(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
   return 0;
 }
 
-// ------------------------------------------------------------------ More'-Thuente step (dcstep)
-LB_HD void lb_dcstep(double &stx, double &fx, double &dx, double &sty, double &fy, double &dy,
-                     double &stp, double fp, double dp, int &brackt, double stpmin, double stpmax) {
-  const double sgnd = dp * (dx / fabs(dx));
-  double stpf;
-  if (fp > fx) {
-    const double theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
-    const double s = fmax(fabs(theta), fmax(fabs(dx), fabs(dp)));
-    double gamma = s * sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
-    if (stp < stx) gamma = -gamma;
-    const double p = (gamma - dx) + theta;
-    const double q = ((gamma - dx) + gamma) + dp;
-    const double r = p / q;
-    const double stpc = stx + r * (stp - stx);
-    const double stpq = stx + ((dx / ((fx - fp) / (stp - stx) + dx)) / 2.0) * (stp - stx);
-    if (fabs(stpc - stx) < fabs(stpq - stx)) stpf = stpc;
-    else stpf = stpc + (stpq - stpc) / 2.0;
-    brackt = 1;
-  } else if (sgnd < 0.0) {
-    const double theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
-    const double s = fmax(fabs(theta), fmax(fabs(dx), fabs(dp)));
-    double gamma = s * sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
-    if (stp > stx) gamma = -gamma;
-    const double p = (gamma - dp) + theta;
-    const double q = ((gamma - dp) + gamma) + dx;
-    const double r = p / q;
-    const double stpc = stp + r * (stx - stp);
-    const double stpq = stp + (dp / (dp - dx)) * (stx - stp);
-    if (fabs(stpc - stp) > fabs(stpq - stp)) stpf = stpc;
-    else stpf = stpq;
-    brackt = 1;
-  } else if (fabs(dp) < fabs(dx)) {
-    const double theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
-    const double s = fmax(fabs(theta), fmax(fabs(dx), fabs(dp)));
-    double gamma = s * sqrt(fmax(0.0, (theta / s) * (theta / s) - (dx / s) * (dp / s)));
-    if (stp > stx) gamma = -gamma;
-    const double p = (gamma - dp) + theta;
-    const double q = (gamma + (dx - dp)) + gamma;
-    const double r = p / q;
-    double stpc;
-    if (r < 0.0 && gamma != 0.0) stpc = stp + r * (stx - stp);
-    else if (stp > stx) stpc = stpmax;
-    else stpc = stpmin;
-    const double stpq = stp + (dp / (dp - dx)) * (stx - stp);
-    if (brackt) {
-      if (fabs(stpc - stp) < fabs(stpq - stp)) stpf = stpc;
-      else stpf = stpq;
-      if (stp > stx) stpf = fmin(stp + 0.66 * (sty - stp), stpf);
-      else stpf = fmax(stp + 0.66 * (sty - stp), stpf);
-    } else {
-      if (fabs(stpc - stp) > fabs(stpq - stp)) stpf = stpc;
-      else stpf = stpq;
-      stpf = fmin(stpmax, stpf);
-      stpf = fmax(stpmin, stpf);
-    }
-  } else {
-    if (brackt) {
-      const double theta = 3.0 * (fp - fy) / (sty - stp) + dy + dp;
-      const double s = fmax(fabs(theta), fmax(fabs(dy), fabs(dp)));
-      double gamma = s * sqrt((theta / s) * (theta / s) - (dy / s) * (dp / s));
-      if (stp > sty) gamma = -gamma;
-      const double p = (gamma - dp) + theta;
-      const double q = ((gamma - dp) + gamma) + dy;
-      const double r = p / q;
-      stpf = stp + r * (sty - stp);
-    } else if (stp > stx) {
-      stpf = stpmax;
-    } else {
-      stpf = stpmin;
-    }
-  }
-  if (fp > fx) {
-    sty = stp; fy = fp; dy = dp;
-  } else {
-    if (sgnd < 0.0) { sty = stx; fy = fx; dy = dx; }
-    stx = stp; fx = fp; dx = dp;
-  }
-  stp = stpf;
-}
-
-// ------------------------------------------------------------------ line search (dcsrch)
-// ftol 1e-3, gtol 0.9, xtol 0.1, stpmin 0 -- the constants lnsrlb passes.
-LB_HD void lb_dcsrch(LbScal &s, double f, double g) {
-  const double ftol = 1e-3, gtol = 0.9, xtol = 0.1, stpmin = 0.0;
-  const double stpmax = s.stpmx;
-  const double xtrapl = 1.1, xtrapu = 4.0;
-  if (s.ls_task == LB_LS_START) {
-    if (s.stp < stpmin || s.stp > stpmax || g >= 0.0) { s.ls_task = LB_LS_ERROR; return; }
-    s.brackt = 0;
-    s.stage = 1;
-    s.finit = f; s.ginit = g; s.gtest = ftol * g;
-    s.width = stpmax - stpmin;
-    s.width1 = s.width / 0.5;
-    s.stx = 0.0; s.fx = f; s.gx = g;
-    s.sty = 0.0; s.fy = f; s.gy = g;
-    s.stmin = 0.0;
-    s.stmax = s.stp + xtrapu * s.stp;
-    s.ls_task = LB_LS_FG;
-    return;
-  }
-  const double ftest = s.finit + s.stp * s.gtest;
-  if (s.stage == 1 && f <= ftest && g >= 0.0) s.stage = 2;
-  int task = LB_LS_FG;
-  if (s.brackt && (s.stp <= s.stmin || s.stp >= s.stmax)) task = LB_LS_WARN;
-  if (s.brackt && s.stmax - s.stmin <= xtol * s.stmax) task = LB_LS_WARN;
-  if (s.stp == stpmax && f <= ftest && g <= s.gtest) task = LB_LS_WARN;
-  if (s.stp == stpmin && (f > ftest || g >= s.gtest)) task = LB_LS_WARN;
-  if (f <= ftest && fabs(g) <= gtol * (-s.ginit)) task = LB_LS_CONV;
-  if (task != LB_LS_FG) { s.ls_task = task; return; }
-  if (s.stage == 1 && f <= s.fx && f > ftest) {
-    const double fm = f - s.stp * s.gtest;
-    double fxm = s.fx - s.stx * s.gtest, fym = s.fy - s.sty * s.gtest;
-    const double gm = g - s.gtest;
-    double gxm = s.gx - s.gtest, gym = s.gy - s.gtest;
-    lb_dcstep(s.stx, fxm, gxm, s.sty, fym, gym, s.stp, fm, gm, s.brackt, s.stmin, s.stmax);
-    s.fx = fxm + s.stx * s.gtest;
-    s.fy = fym + s.sty * s.gtest;
-    s.gx = gxm + s.gtest;
-    s.gy = gym + s.gtest;
-  } else {
-    lb_dcstep(s.stx, s.fx, s.gx, s.sty, s.fy, s.gy, s.stp, f, g, s.brackt, s.stmin, s.stmax);
-  }
-  if (s.brackt) {
-    if (fabs(s.sty - s.stx) >= 0.66 * s.width1) s.stp = s.stx + 0.5 * (s.sty - s.stx);
-    s.width1 = s.width;
-    s.width = fabs(s.sty - s.stx);
-  }
-  if (s.brackt) {
-    s.stmin = fmin(s.stx, s.sty);
-    s.stmax = fmax(s.stx, s.sty);
-  } else {
-    s.stmin = s.stp + xtrapl * (s.stp - s.stx);
-    s.stmax = s.stp + xtrapu * (s.stp - s.stx);
-  }
-  s.stp = fmax(s.stp, stpmin);
-  s.stp = fmin(s.stp, stpmax);
-  if ((s.brackt && (s.stp <= s.stmin || s.stp >= s.stmax)) ||
-      (s.brackt && s.stmax - s.stmin <= xtol * s.stmax))
-    s.stp = s.stx;
-  s.ls_task = LB_LS_FG;
-}
-
 // ------------------------------------------------------------------ BFGS memory update (matupd)
 // Columns are kept in logical order (0 = oldest): when the memory is full everything is
-// shifted by one instead of rotating a head pointer.
-LB_HD void lb_matupd(const LbParams &P, LbWork &w, LbScal &s, double rr, double dr) {
+// shifted by one instead of rotating a head pointer.  On entry w.r = y (new), w.d = s (new),
+// rr = y'y, dr = y's.  SY, SS and YY are maintained as full matrices (see LbWork).
+LB_FN void lb_matupd(const LbParams &P, LbWork &w, LbScal &s, double rr, double dr) {
   const int n = P.n, m = P.m, ldw = LB_LDW(m);
   LB_SYNC();
   if (s.iupdat <= m) {
     s.col = s.iupdat;
   } else {
     LB_FOR(i, n) {
-      double *row = w.W + i * ldw;
+      LbDP row = w.W + i * ldw;
       for (int j = 0; j < m - 1; ++j) { row[j] = row[j + 1]; row[m + j] = row[m + j + 1]; }
     }
-    // new(i,j) = old(i+1,j+1): one lane per diagonal, walking down it
+    // new(i,j) = old(i+1,j+1) for the three (m-1) x (m-1) leading blocks: lane j owns column j
+    // and walks down it, so every read of a column happens before the write that replaces it
+    // comes from the column to its right (owned by lane j+1) -- hence read all, sync, write all
     const int c1 = s.col - 1;
-    for (int dg = LB_LANE; dg < 2 * c1; dg += LB_NL) {
-      if (dg < c1) {  // ss upper: j - i = dg
-        for (int i = 0; i + dg < c1; ++i) w.ss[i * m + i + dg] = w.ss[(i + 1) * m + i + dg + 1];
-      } else {        // sy lower: i - j = dg - c1
-        const int e = dg - c1;
-        for (int j = 0; j + e < c1; ++j) w.sy[(j + e) * m + j] = w.sy[(j + e + 1) * m + j + 1];
+    LbDP mats[3] = {w.sy, w.ss, w.yy};
+    for (int q = 0; q < 3; ++q) {
+      LbDP A = mats[q];
+      for (int i = 0; i < c1; ++i) {
+        double tmp = 0.0;
+        const int j = LB_LANE;
+#if LB_WARP
+        if (j < c1) tmp = A[(i + 1) * m + j + 1];
+        LB_SYNC();
+        if (j < c1) A[i * m + j] = tmp;
+#else
+        for (int jj = 0; jj < c1; ++jj) A[i * m + jj] = A[(i + 1) * m + jj + 1];
+        (void)tmp; (void)j;
+#endif
       }
     }
   }
@@ -811,64 +862,61 @@ LB_HD void lb_matupd(const LbParams &P, LbWork &w, LbScal &s, double rr, double 
   }
   s.theta = rr / dr;
   LB_SYNC();
-  // last row of SY, last column of SS
-  for (int j = LB_LANE; j < 2 * last; j += LB_NL) {
-    if (j < last) {
-      double a = 0.0;
-      for (int i = 0; i < n; ++i) a += w.d[i] * w.W[i * ldw + j];
-      w.sy[last * m + j] = a;
-    } else {
-      const int jj = j - last;
-      double a = 0.0;
-      for (int i = 0; i < n; ++i) a += w.W[i * ldw + m + jj] * w.d[i];
-      w.ss[jj * m + last] = a;
+  // products of the new pair with every older column j: lane j < last pairs y_j with (s,y),
+  // lane last + j pairs s_j with (s,y)
+  for (int jl = LB_LANE; jl < 2 * last; jl += LB_NL) {
+    const bool is_y = jl < last;
+    const int j = is_y ? jl : jl - last;
+    const LbDP colp = w.W + (is_y ? j : m + j);
+    double a_s = 0.0, a_y = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const double c = colp[i * ldw];
+      a_s += w.d[i] * c;
+      a_y += w.r[i] * c;
+    }
+    if (is_y) {  // y_j . s_new,  y_j . y_new
+      w.sy[last * m + j] = a_s;
+      w.yy[last * m + j] = a_y;
+      w.yy[j * m + last] = a_y;
+    } else {     // s_j . s_new,  s_j . y_new
+      w.ss[j * m + last] = a_s;
+      w.ss[last * m + j] = a_s;
+      w.sy[j * m + last] = a_y;
     }
   }
   if (LB_LANE == 0) {
     w.ss[last * m + last] = s.stp == 1.0 ? s.dtd : s.stp * s.stp * s.dtd;
     w.sy[last * m + last] = dr;
+    w.yy[last * m + last] = rr;
   }
   LB_SYNC();
-}
-
-LB_HD void lb_reset_memory(LbScal &s) {
-  s.col = 0;
-  s.theta = 1.0;
-  s.iupdat = 0;
-  s.updatd = 0;
-}
-
-// ------------------------------------------------------------------ the stepper
-// Advance one start until it needs f,g at a new point (returns 1: trial point is in w.x)
-// or terminates (returns 0: s.status/s.task set, final iterate in w.x).
-//
-// On entry w.x holds the point that was just evaluated, s.f / w.g its value and gradient
-// (already stored by the caller), and the persisted vectors/matrices are loaded.
-// `x_eval_changed` reports whether the new request differs from the point evaluated last
-// (SciPy's ScalarFunction memoises on x, so a repeated request does not count in nfev).
-LB_HD void lb_finish(LbScal &s, int status, int task) {
-  s.phase = LB_PH_DONE;
-  s.status = status;
-  s.task = task;
 }
 
 // `Mem` supplies the limited-memory matrices lazily: mem.load() is called once, right before
 // they are first needed (a step that only continues a line search never touches them), and
 // mem.dirty() when they were modified.
 struct LbNoMem {
-  LB_HD void load() {}
-  LB_HD void dirty() {}
-  LB_HD void dirty_vec() {}
+  LB_FN void load() {}
+  LB_FN void dirty() {}
+  LB_FN void dirty_vec() {}
 };
 
+//
+// `stage` splits a step in two so that the cheap and the expensive halves can be scheduled
+// separately: 0 = the whole step (what the product's kernel runs); 1 = LIGHT: consume f,g, run the line-search
+// logic and, if the search goes on, post the next trial point (returns 1) -- if a new
+// iteration has to be set up instead it records where to resume in s.resume and returns 2
+// without touching the limited-memory matrices; 2 = HEAVY: resume there.
 template <class Mem>
-LB_HD int lb_advance(const LbParams &P, LbWork &w, LbScal &s, Mem &mem) {
+LB_FN int lb_advance(const LbParams &P, LbWork &w, LbScal &s, Mem &mem, int stage = 0) {
   const int n = P.n, m = P.m;
   enum { ST_TESTS, ST_ITER, ST_REQUEST, ST_FAIL };
   int st;
 
   if (s.phase == LB_PH_DONE) return 0;
-  if (s.phase == LB_PH_START) {
+  if (stage == 2) {
+    st = s.resume;
+  } else if (s.phase == LB_PH_START) {
     s.sbgnrm = lb_projgr(P, w.x, w.g);
     if (s.sbgnrm <= P.pgtol) { lb_finish(s, 0, 401); return 0; }
     st = ST_ITER;
@@ -895,12 +943,15 @@ LB_HD int lb_advance(const LbParams &P, LbWork &w, LbScal &s, Mem &mem) {
   }
 
   for (;;) {
-    if (st == ST_TESTS || st == ST_ITER) mem.load();
     if (st == ST_TESTS) {
       // ---- termination tests (mainlb label 777) ----
       if (s.sbgnrm <= P.pgtol) { lb_finish(s, 0, 401); return 0; }
       const double ddum = fmax(fabs(s.fold), fmax(fabs(s.f), 1.0));
       if (s.fold - s.f <= P.ftol * ddum) { lb_finish(s, 0, 402); return 0; }
+    }
+    if (stage == 1 && st != ST_REQUEST) { s.resume = st; return 2; }
+    if (st == ST_TESTS || st == ST_ITER) mem.load();
+    if (st == ST_TESTS) {
       // ---- y = g - gold, s = x - xold ----
       double rr = 0.0;
       LB_FOR(i, n) { const double y = w.g[i] - w.r[i]; w.r[i] = y; rr += y * y; }
@@ -922,7 +973,7 @@ LB_HD int lb_advance(const LbParams &P, LbWork &w, LbScal &s, Mem &mem) {
         s.iupdat += 1;
         mem.dirty();
         lb_matupd(P, w, s, rr, dr);
-        if (lb_formt(w.wt, w.sy, w.ss, m, s.col, s.theta)) lb_reset_memory(s);
+        if (lb_formt(w, m, s.col, s.theta)) lb_reset_memory(s);
       }
       st = ST_ITER;
     }
@@ -1031,6 +1082,7 @@ LB_HD int lb_advance(const LbParams &P, LbWork &w, LbScal &s, Mem &mem) {
     }
 
     // ST_FAIL: restore the previous iterate
+    if (stage == 1) { s.resume = ST_FAIL; return 2; }
     LB_SYNC();
     LB_FOR(i, n) { w.x[i] = w.t[i]; w.g[i] = w.r[i]; }
     s.f = s.fold;
@@ -1046,7 +1098,7 @@ LB_HD int lb_advance(const LbParams &P, LbWork &w, LbScal &s, Mem &mem) {
 }
 
 // Set up a start: project x0 into the box, classify the variables (active).
-LB_HD void lb_init_state(const LbParams &P, LbWork &w, LbScal &s) {
+LB_FN void lb_init_state(const LbParams &P, LbWork &w, LbScal &s) {
   const int n = P.n;
   LB_FOR(i, n) {
     double xi = w.x[i];
@@ -1068,5 +1120,5 @@ LB_HD void lb_init_state(const LbParams &P, LbWork &w, LbScal &s) {
   s.stx = s.sty = s.stmin = s.stmax = s.width = s.width1 = 0;
   s.phase = LB_PH_START; s.col = 0; s.iupdat = 0; s.iter = 0; s.nit = 0; s.nfev = 0;
   s.ifun = 0; s.iback = 0; s.updatd = 0; s.status = -1; s.task = 0;
-  s.brackt = 0; s.stage = 0; s.ls_task = LB_LS_START; s.nskip = 0; s.nintol = 0;
+  s.brackt = 0; s.stage = 0; s.ls_task = LB_LS_START; s.nskip = 0; s.nintol = 0; s.resume = 0;
 }

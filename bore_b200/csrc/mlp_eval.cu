@@ -106,6 +106,10 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
   extern __shared__ __align__(16) float smem[];
   const int G = d.n_layers - 1;
   const int tid = threadIdx.x, nthr = blockDim.x;
+  // CTAs with no tile leave before paying for the weight staging: late L-BFGS-B rounds have
+  // few active starts, and the launch is sized for all S of them
+  const int n = n_dev ? min(*n_dev, S) : S;
+  if (blockIdx.x * (nthr >> 5) * TP >= n) return;
 
   // ---- stage weights (zero padded) ----
   for (int l = 0; l < G; ++l) {
@@ -137,7 +141,6 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
   const int act_last = d.act[G];
   __syncthreads();
 
-  const int n = n_dev ? min(*n_dev, S) : S;
   const int n_tiles = (n + TP - 1) / TP;
   const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
   const int ug = lane & 7, pg = lane >> 3;

@@ -5,9 +5,11 @@
 #include <string.h>
 #include <vector>
 
+#define LB_VARIANT 0
 #include "../../bore_b200/csrc/lbfgsb_core.h"
 
 struct HostSim {
+  int split = 0;  // 1: run every step as a LIGHT stage followed, if asked for, by a HEAVY stage
   LbParams P;
   std::vector<double> lo, hi, dbuf, xlast;
   std::vector<int> nbd, ibuf;
@@ -43,6 +45,7 @@ void *hs_create(int n, int m, const double *lo, const double *hi, double ftol, d
 }
 
 void hs_destroy(void *p) { delete (HostSim *)p; }
+void hs_set_split(void *p, int on) { ((HostSim *)p)->split = on; }
 
 // returns 1; xreq = first request (x0 projected)
 int hs_start(void *p, const double *x0, double *xreq) {
@@ -62,7 +65,13 @@ int hs_step(void *p, double f, const double *g, double *xreq) {
   h->s.f = f;
   memcpy(h->w.g, g, n * sizeof(double));
   LbNoMem nomem;
-  const int pend = lb_advance(h->P, h->w, h->s, nomem);
+  int pend;
+  if (h->split) {
+    pend = lb_advance(h->P, h->w, h->s, nomem, 1);
+    if (pend == 2) pend = lb_advance(h->P, h->w, h->s, nomem, 2);
+  } else {
+    pend = lb_advance(h->P, h->w, h->s, nomem);
+  }
   if (pend) {
     bool same = true;
     for (int i = 0; i < n; ++i) same = same && (h->w.x[i] == h->xlast[i]);

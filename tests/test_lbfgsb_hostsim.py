@@ -23,8 +23,9 @@ dp = C.POINTER(C.c_double)
 def hs():
     src = os.path.join(HERE, "hostsim", "lbfgsb_hostsim.cpp")
     so = os.path.join(HERE, "hostsim", "libhostsim.so")
-    core = os.path.join(HERE, "..", "bore_b200", "csrc", "lbfgsb_core.h")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
+    deps = [src] + [os.path.join(HERE, "..", "bore_b200", "csrc", f)
+                    for f in ("lbfgsb_core.h", "lbfgsb_types.h")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", so, src])
     lib = C.CDLL(so)
     lib.hs_create.restype = C.c_void_p
@@ -33,6 +34,7 @@ def hs():
     lib.hs_step.argtypes = [C.c_void_p, C.c_double, dp, dp]
     lib.hs_result.argtypes = [C.c_void_p, dp, dp] + [C.POINTER(C.c_int)] * 4
     lib.hs_destroy.argtypes = [C.c_void_p]
+    lib.hs_set_split.argtypes = [C.c_void_p, C.c_int]
     return lib
 
 
@@ -40,7 +42,7 @@ def _P(a):
     return a.ctypes.data_as(dp)
 
 
-def _run(hs, w, acts, transform, X0, lo, hi, maxiter=1000):
+def _run(hs, w, acts, transform, X0, lo, hi, maxiter=1000, split=False):
     S, n = X0.shape
     keys = ("x", "fun", "nit", "nfev", "status")
     got = dict(x=np.zeros((S, n)), fun=np.zeros(S), nit=np.zeros(S, int), nfev=np.zeros(S, int),
@@ -49,6 +51,7 @@ def _run(hs, w, acts, transform, X0, lo, hi, maxiter=1000):
     max_req_dx = np.zeros(S)
     for s in range(S):
         h = hs.hs_create(n, 10, _P(lo), _P(hi), 1e-9, 1e-5, maxiter, 15000, 20)
+        hs.hs_set_split(h, 1 if split else 0)
         ls = am.LockstepLBFGSB(X0[s:s + 1], lo, hi, maxiter=maxiter)
         xr = np.zeros(n)
         pend = hs.hs_start(h, _P(np.ascontiguousarray(X0[s])), _P(xr))
@@ -77,13 +80,16 @@ def _run(hs, w, acts, transform, X0, lo, hi, maxiter=1000):
     return got, ref
 
 
+@pytest.mark.parametrize("split", [False, True])
 @pytest.mark.parametrize("name", ["cfg5_plugin8", "tanh_exp"])
-def test_smooth_objectives_track_setulb(hs, name):
+def test_smooth_objectives_track_setulb(hs, name, split):
+    """`split` runs every step as the LIGHT stage + (if requested) the HEAVY stage, the way the
+    thread-per-start kernel does."""
     dims, acts, transform = NETS[name]
     n = dims[0]
     w = trained_weights(dims, acts, seed=1)
     X0 = np.random.RandomState(2).uniform(size=(40, n))
-    got, ref = _run(hs, w, acts, transform, X0, np.zeros(n), np.ones(n))
+    got, ref = _run(hs, w, acts, transform, X0, np.zeros(n), np.ones(n), split=split)
     assert np.array_equal(got["status"], ref["status"])
     assert np.abs(got["fun"] - ref["fun"]).max() <= 1e-7
     assert np.abs(got["x"] - ref["x"]).max() <= 1e-6
@@ -98,7 +104,7 @@ def test_relu_objectives_agree_at_the_north_star_rate(hs, name):
     w = trained_weights(dims, acts, seed=1)
     S = 64 if n < 50 else 24
     X0 = np.random.RandomState(2).uniform(size=(S, n))
-    got, ref = _run(hs, w, acts, transform, X0, np.zeros(n), np.ones(n))
+    got, ref = _run(hs, w, acts, transform, X0, np.zeros(n), np.ones(n), split=(n == 6))
     agree = np.abs(got["fun"] - ref["fun"]) <= 1e-4
     assert agree.mean() >= 0.90, agree.mean()
     assert np.mean(got["status"] == ref["status"]) >= 0.90
