@@ -292,6 +292,17 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_kernel(const FitArgs a) {
             int kk[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) kk[u] = min(tk + u * tkn, in - 1);
+            // Adam slots of this tile: requested from L2 now, consumed after the GEMM loop, so
+            // their latency hides behind the accumulation
+            float am[4][4], av[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int gi = d.w_off[l] + kk[i] * out + min(tj * 4 + u, out - 1);
+                am[i][u] = __ldcg(gm + gi);
+                av[i][u] = __ldcg(gv + gi);
+              }
             for (int p = 0; p < BP; p += 4) {
               float4 hv[4], dv[4];
 #pragma unroll
@@ -321,7 +332,7 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_kernel(const FitArgs a) {
                 float wv = W[k * JP + j];
                 float g = acc[i][u];
                 if (l2k != 0.f) { reg += l2k * wv * wv; g += 2.f * l2k * wv; }
-                float m = gm[gi], v = gv[gi];
+                float m = am[i][u], v = av[i][u];
                 m += (g - m) * om1;
                 v += (g * g - v) * om2;
                 wv -= (m * alpha) / (sqrtf(v) + a.eps);

@@ -16,12 +16,23 @@
 // bound, not shared-memory bound.  The reverse pass reuses the same loop on WT and
 // multiplies by act'(h) (expressed through the stored layer output, as TF's *Grad kernels
 // do) in the epilogue, overwriting the activation strip in place.
+//
+// Two lane mappings (template UGB): 8 unit-groups x 4 point-groups (tiles of 16 points, 32-unit
+// chunks) for hidden widths <= 32, and 16 unit-groups x 2 point-groups (tiles of 8 points,
+// 64-unit chunks) for wider layers -- the per-warp strip is half as large there, which doubles
+// the warps that fit beside the weights in shared memory.
 #include "common.cuh"
 
 namespace {
 
-constexpr int TP = 16;   // points per warp tile
-constexpr int AST = 20;  // activation strip row stride (floats): conflict-free float4 rows
+template <int UGB>
+struct Map {
+  static constexpr int UG = 1 << UGB;        // lanes across units
+  static constexpr int PG = 32 >> UGB;       // lanes across points
+  static constexpr int TP = 4 * PG;          // points per warp tile
+  static constexpr int CH = 4 * UG;          // units per chunk
+  static constexpr int AST = TP + 4;         // activation strip row stride (floats)
+};
 
 __device__ __forceinline__ float act_fwd(int a, float v) {
   switch (a) {
@@ -56,25 +67,26 @@ struct SmemPlan {
 
 __host__ __device__ inline int rup(int a, int b) { return (a + b - 1) / b * b; }
 
-__host__ __device__ inline void make_plan(const MlpDesc &d, bool grad, SmemPlan &p) {
+__host__ __device__ inline void make_plan(const MlpDesc &d, bool grad, int CH, int AST, SmemPlan &p) {
   int off = 0;
   const int G = d.n_layers - 1;  // GEMM (hidden) layers
   for (int l = 0; l < G; ++l) {
     int in = d.dims[l], out = d.dims[l + 1];
-    p.wf[l] = off; off += rup(in, 4) * rup(out, 32);
-    p.bias[l] = off; off += rup(out, 32);
-    p.wb[l] = off; if (grad) off += rup(out, 4) * rup(in, 32);
+    p.wf[l] = off; off += rup(in, 4) * rup(out, CH);
+    p.bias[l] = off; off += rup(out, CH);
+    p.wb[l] = off; if (grad) off += rup(out, 4) * rup(in, CH);
   }
-  p.wl_len = G > 0 ? rup(d.dims[G], 32) : rup(d.dims[0], 8);
+  p.wl_len = G > 0 ? rup(d.dims[G], CH) : rup(d.dims[0], CH / 4);
   p.wl = off; off += p.wl_len;
   p.weights_total = rup(off, 4);
   int w = 0;
-  p.buf[0] = 0; w += AST * (G > 0 ? rup(d.dims[0], 4) : rup(d.dims[0], 8));
-  for (int l = 1; l <= G; ++l) { p.buf[l] = w; w += AST * rup(d.dims[l], 32); }
+  p.buf[0] = 0; w += AST * (G > 0 ? rup(d.dims[0], 4) : p.wl_len);
+  for (int l = 1; l <= G; ++l) { p.buf[l] = w; w += AST * rup(d.dims[l], CH); }
   p.warp_total = w;
 }
 
 // acc[i][u] += sum_k A[k][pg*4+i] * W[k][col0+u],  k < K4 (multiple of 4)
+template <int AST>
 __device__ __forceinline__ void tile_gemm(const float *__restrict__ A, const float *__restrict__ W,
                                           int K4, int ldw, float (&acc)[4][4]) {
 #pragma unroll 2
@@ -97,13 +109,15 @@ __device__ __forceinline__ void tile_gemm(const float *__restrict__ A, const flo
   }
 }
 
-template <bool GRAD>
+template <bool GRAD, int UGB>
 __global__ void __launch_bounds__(512)
 mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ params,
                 const float *__restrict__ X,
                 int S, const int *__restrict__ n_dev, const int *__restrict__ list,
                 float *__restrict__ f_out, float *__restrict__ g_out, int transform, float sign) {
   extern __shared__ __align__(16) float smem[];
+  using M = Map<UGB>;
+  constexpr int TP = M::TP, AST = M::AST, CH = M::CH, UG = M::UG;
   const int G = d.n_layers - 1;
   const int tid = threadIdx.x, nthr = blockDim.x;
   // CTAs with no tile leave before paying for the weight staging: late L-BFGS-B rounds have
@@ -114,7 +128,7 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
   // ---- stage weights (zero padded) ----
   for (int l = 0; l < G; ++l) {
     const int in = d.dims[l], out = d.dims[l + 1];
-    const int in4 = rup(in, 4), outP = rup(out, 32);
+    const int in4 = rup(in, 4), outP = rup(out, CH);
     const float *Wg = params + d.w_off[l];
     float *wf = smem + P.wf[l];
     for (int e = tid; e < in4 * outP; e += nthr) {
@@ -124,7 +138,7 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
     float *bs = smem + P.bias[l];
     for (int e = tid; e < outP; e += nthr) bs[e] = e < out ? params[d.b_off[l] + e] : 0.f;
     if (GRAD) {
-      const int out4 = rup(out, 4), inP = rup(in, 32);
+      const int out4 = rup(out, 4), inP = rup(in, CH);
       float *wb = smem + P.wb[l];
       for (int e = tid; e < out4 * inP; e += nthr) {
         int j = e / inP, k = e - j * inP;
@@ -143,7 +157,7 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
 
   const int n_tiles = (n + TP - 1) / TP;
   const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
-  const int ug = lane & 7, pg = lane >> 3;
+  const int ug = lane & (UG - 1), pg = lane >> UGB;
   float *strip = smem + P.weights_total + warp * P.warp_total;
   const int D = d.dims[0];
   const float *wl = smem + P.wl;
@@ -153,7 +167,7 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
     // ---- load the 16 input rows, transposed into buf0[k][p] ----
     {
       float *xb = strip + P.buf[0];
-      const int rows0 = G > 0 ? rup(D, 4) : rup(D, 8);
+      const int rows0 = G > 0 ? rup(D, 4) : P.wl_len;
       for (int pl = 0; pl < TP; ++pl) {
         const int idx = p0 + pl;
         const bool ok = idx < n;
@@ -166,15 +180,15 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
 
     // ---- forward through the hidden layers ----
     for (int l = 0; l < G; ++l) {
-      const int in4 = rup(d.dims[l], 4), outP = rup(d.dims[l + 1], 32);
+      const int in4 = rup(d.dims[l], 4), outP = rup(d.dims[l + 1], CH);
       const float *A = strip + P.buf[l] + pg * 4;
       float *H = strip + P.buf[l + 1];
       const float *W = smem + P.wf[l];
       const float *bs = smem + P.bias[l];
       const int a = d.act[l];
-      for (int c = 0; c < outP; c += 32) {
+      for (int c = 0; c < outP; c += CH) {
         float acc[4][4] = {};
-        tile_gemm(A, W + c + ug * 4, in4, outP, acc);
+        tile_gemm<AST>(A, W + c + ug * 4, in4, outP, acc);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int unit = c + ug * 4 + u;
@@ -193,7 +207,7 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
     // ---- final Dense(1): u = act(h . w + b) for this lane's 4 points ----
     float *HL = strip + P.buf[G];
     float up[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int k = ug; k < P.wl_len; k += 8) {
+    for (int k = ug; k < P.wl_len; k += UG) {
       const float4 hv = *reinterpret_cast<const float4 *>(HL + k * AST + pg * 4);
       const float w = wl[k];
       up[0] = fmaf(hv.x, w, up[0]);
@@ -203,9 +217,8 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      up[i] += __shfl_xor_sync(0xffffffffu, up[i], 1);
-      up[i] += __shfl_xor_sync(0xffffffffu, up[i], 2);
-      up[i] += __shfl_xor_sync(0xffffffffu, up[i], 4);
+#pragma unroll
+      for (int o = 1; o < UG; o <<= 1) up[i] += __shfl_xor_sync(0xffffffffu, up[i], o);
     }
     float dpre[4];
 #pragma unroll
@@ -236,7 +249,7 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
     // ---- reverse: delta of the last hidden layer (elementwise), then GEMMs on WT ----
     if (G == 0) {
       // no hidden layer: g = dpre * w
-      for (int k = ug; k < D; k += 8) {
+      for (int k = ug; k < D; k += UG) {
         const float w = wl[k];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -249,7 +262,7 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
     }
     {
       const int a = d.act[G - 1];
-      for (int k = ug; k < P.wl_len; k += 8) {
+      for (int k = ug; k < P.wl_len; k += UG) {
         float4 hv = *reinterpret_cast<const float4 *>(HL + k * AST + pg * 4);
         const float w = wl[k];
         hv.x = dpre[0] * w * act_bwd(a, hv.x);
@@ -261,15 +274,15 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
     }
     __syncwarp();
     for (int l = G - 1; l >= 0; --l) {
-      const int out4 = rup(d.dims[l + 1], 4), inP = rup(d.dims[l], 32);
+      const int out4 = rup(d.dims[l + 1], 4), inP = rup(d.dims[l], CH);
       const float *A = strip + P.buf[l + 1] + pg * 4;   // delta_out [j][p]
       const float *W = smem + P.wb[l];                  // WT [j][k]
       float *Hin = strip + P.buf[l];
       if (l > 0) {
         const int a = d.act[l - 1];
-        for (int c = 0; c < inP; c += 32) {
+        for (int c = 0; c < inP; c += CH) {
           float acc[4][4] = {};
-          tile_gemm(A, W + c + ug * 4, out4, inP, acc);
+          tile_gemm<AST>(A, W + c + ug * 4, out4, inP, acc);
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             float *hp = Hin + (c + ug * 4 + u) * AST + pg * 4;
@@ -284,9 +297,9 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
         __syncwarp();
       } else {
         // input gradient: stage through buf0 (x is dead) so the global store is coalesced
-        for (int c = 0; c < inP; c += 32) {
+        for (int c = 0; c < inP; c += CH) {
           float acc[4][4] = {};
-          tile_gemm(A, W + c + ug * 4, out4, inP, acc);
+          tile_gemm<AST>(A, W + c + ug * 4, out4, inP, acc);
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int k = c + ug * 4 + u;
@@ -310,13 +323,13 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
 
 }  // namespace
 
-int launch_mlp_eval(const bore_mlp *h, int model, bool want_grad, int transform, int negate,
-                    const float *X, int S, float *f, float *g, const int *list,
-                    const int *n_dev, cudaStream_t stream) {
-  if (S <= 0) return 0;
-  const MlpDesc &d = h->desc;
+template <bool GRAD, int UGB>
+static int launch_variant(const bore_mlp *h, const MlpDesc &d, const float *params, const float *X,
+                          int S, float *f, float *g, const int *list, const int *n_dev,
+                          int transform, float sign, cudaStream_t stream) {
+  using M = Map<UGB>;
   SmemPlan P;
-  make_plan(d, want_grad, P);
+  make_plan(d, GRAD, M::CH, M::AST, P);
   const int max_smem = 227 * 1024;
   // warps per CTA: as many as fit (<= 16), at least 1
   int warps = 16;
@@ -326,7 +339,7 @@ int launch_mlp_eval(const bore_mlp *h, int model, bool want_grad, int transform,
   const size_t smem = (size_t)(P.weights_total + warps * P.warp_total) * sizeof(float);
   BORE_CHECK(smem <= (size_t)max_smem, "mlp_eval: model needs %zu B of shared memory (> %d)",
              smem, max_smem);
-  const int n_tiles = (S + TP - 1) / TP;
+  const int n_tiles = (S + M::TP - 1) / M::TP;
   int ctas_needed = (n_tiles + warps - 1) / warps;
   int per_sm = (int)((size_t)max_smem / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
@@ -334,19 +347,27 @@ int launch_mlp_eval(const bore_mlp *h, int model, bool want_grad, int transform,
   int grid = h->sm_count * per_sm;
   if (grid > ctas_needed) grid = ctas_needed;
   if (grid < 1) grid = 1;
-  const float *params = h->params + (size_t)model * d.n_params;
-  const float sign = negate ? -1.f : 1.f;
-  if (want_grad) {
-    BORE_CUDA(cudaFuncSetAttribute(mlp_eval_kernel<true>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_eval_kernel<true><<<grid, warps * 32, smem, stream>>>(d, P, params, X, S, n_dev, list, f, g,
-                                                             transform, sign);
-  } else {
-    BORE_CUDA(cudaFuncSetAttribute(mlp_eval_kernel<false>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_eval_kernel<false><<<grid, warps * 32, smem, stream>>>(d, P, params, X, S, n_dev, list, f, g,
-                                                              transform, sign);
-  }
+  BORE_CUDA(cudaFuncSetAttribute(mlp_eval_kernel<GRAD, UGB>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mlp_eval_kernel<GRAD, UGB><<<grid, warps * 32, smem, stream>>>(d, P, params, X, S, n_dev, list, f, g,
+                                                               transform, sign);
   BORE_CUDA(cudaGetLastError());
   return 0;
+}
+
+int launch_mlp_eval(const bore_mlp *h, int model, bool want_grad, int transform, int negate,
+                    const float *X, int S, float *f, float *g, const int *list,
+                    const int *n_dev, cudaStream_t stream) {
+  if (S <= 0) return 0;
+  const MlpDesc &d = h->desc;
+  int widest = 0;
+  for (int l = 1; l < d.n_layers; ++l) widest = d.dims[l] > widest ? d.dims[l] : widest;
+  const bool wide = widest > 32;  // 64-unit chunks, tiles of 8 points
+  const float *params = h->params + (size_t)model * d.n_params;
+  const float sign = negate ? -1.f : 1.f;
+  if (want_grad)
+    return wide ? launch_variant<true, 4>(h, d, params, X, S, f, g, list, n_dev, transform, sign, stream)
+                : launch_variant<true, 3>(h, d, params, X, S, f, g, list, n_dev, transform, sign, stream);
+  return wide ? launch_variant<false, 4>(h, d, params, X, S, f, g, list, n_dev, transform, sign, stream)
+              : launch_variant<false, 3>(h, d, params, X, S, f, g, list, n_dev, transform, sign, stream);
 }
