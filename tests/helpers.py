@@ -34,3 +34,31 @@ def trained_weights(dims, acts, seed=0, N=300, epochs=30, gamma=0.25):
         acts_fit[-1] = "linear"
     km.fit(w, acts_fit, X, z, epochs, 64, perms)
     return w
+
+
+def permuted_units(weights, seed=0):
+    """The same network with the hidden units of every hidden layer permuted: mathematically the
+    identical function, but every dot product is summed in a different order -- an fp32
+    re-association of the kind any other implementation of the same MLP (TensorFlow's Eigen
+    kernels, this NumPy oracle, a CUDA kernel) differs by."""
+    rs = np.random.RandomState(seed)
+    ws = [np.array(w) for w in weights]
+    n_layers = len(ws) // 2
+    for l in range(n_layers - 1):
+        perm = rs.permutation(ws[2 * l].shape[1])
+        ws[2 * l] = ws[2 * l][:, perm]
+        ws[2 * l + 1] = ws[2 * l + 1][perm]
+        ws[2 * l + 2] = ws[2 * l + 2][perm, :]
+    return ws
+
+
+def reference_self_agreement(weights, acts, X0, bounds, transform, tol, ref=None):
+    """Fraction of starts on which the reference path (oracle MLP + SciPy L-BFGS-B) reaches the
+    same objective value (within tol) as ITSELF after an fp32 re-association of the MLP.  On
+    piecewise-linear (ReLU) objectives this is well below 1 -- the yardstick for what "agrees
+    with the reference" can mean there."""
+    from oracle import argmax as am
+    if ref is None:
+        ref = am.minimize_starts(weights, acts, X0, bounds, transform=transform)
+    alt = am.minimize_starts(permuted_units(weights), acts, X0, bounds, transform=transform)
+    return float(np.mean(np.abs(alt["fun"] - ref["fun"]) <= tol)), ref, alt
