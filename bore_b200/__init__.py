@@ -12,3 +12,4 @@ from .models import (Sequential, DenseSequential, MaximizableModel,  # noqa: F40
                      MaximizableSequential, MaximizableDenseSequential)
 from .data import Record  # noqa: F401
 from .math import steps_per_epoch, ceil_divide  # noqa: F401
+from .batched import BatchedMaximizableSequential, problem_shard  # noqa: F401

@@ -54,6 +54,13 @@ SIGNATURES = {
     "bore_topk_smallest": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_size_t, C.c_int, vp]),
     "bore_topk_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "bore_select_best": (C.c_int, [vp, vp, vp, C.c_int, C.c_int64, vp, C.c_int, vp]),
+    "bore_mlp_predict_multi": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp]),
+    "bore_topk_smallest_groups": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]),
+    "bore_lbfgsb_minimize_multi": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int,
+                                             C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
+                                             vp, C.c_size_t, vp, vp, vp, vp, vp, vp,
+                                             c_int_p, C.POINTER(C.c_longlong), vp]),
+    "bore_select_best_groups": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, C.c_int, vp]),
     "bore_bench_ffma_peak": (C.c_int, [C.c_int, C.c_int, c_double_p]),
 }
 

@@ -1,0 +1,172 @@
+"""Batched BO problems (build extension; BASELINE.json configs[3]).
+
+The reference runs ONE problem per Python process: ``classifier.fit(X, z)`` then
+``classifier.argmax(...)`` (README.rst:83-103).  ``BatchedMaximizableSequential`` holds M
+independent classifiers of one architecture -- seeds of a benchmark, concurrent optimisations,
+per-budget classifiers -- and advances all of them with the same kernels in the same launches:
+training is one CTA per model (``bore_mlp_fit``), screening / top-k / selection are grouped by
+model, and the L-BFGS-B stepper sees M * num_starts starts.  Per problem the semantics are the
+reference's own ``fit`` and ``argmax`` (bore/mixins.py:22-89); problems share nothing, so sharding
+them over GPUs (``problem_shard``) needs no collective.
+"""
+import numpy as np
+from scipy.optimize import OptimizeResult
+from sklearn.utils import check_random_state
+
+from . import ops
+from .engine import NativeMLP, lbfgsb_message
+from .layers import Dense, BinaryCrossentropy, Adam
+from .optimizers.utils import from_bounds
+
+
+def problem_shard(n_problems, rank, world):
+    """Contiguous block [lo, hi) of problems owned by ``rank`` (no data-path collective)."""
+    from .distributed import shard_bounds
+    return shard_bounds(n_problems, rank, world)
+
+
+class BatchedMaximizableSequential:
+
+    def __init__(self, layers, n_problems, transform=ops.identity, seed=None, device=None):
+        self.layers = list(layers)
+        assert self.layers and all(isinstance(l, Dense) for l in self.layers)
+        assert self.layers[0].input_dim is not None, "the first Dense layer needs input_dim"
+        self.n_problems = int(n_problems)
+        dims = [self.layers[0].input_dim] + [l.units for l in self.layers]
+        acts = [l.activation for l in self.layers]
+        self.dims, self.acts = dims, acts
+        e = transform(-ops.Expr(self, (1,), (1,)))
+        if not isinstance(e, ops.Expr) or e.sign != -1:
+            raise NotImplementedError("transform must be one of bore_b200.ops.identity/sigmoid/exp")
+        self._transform = e.transform
+        self._net = NativeMLP(dims, acts, n_models=self.n_problems, device=device)
+        self._rs = np.random.RandomState(seed)
+        self._compiled = False
+        for p in range(self.n_problems):  # glorot_uniform kernels, zero biases, per problem
+            ws = []
+            for fi, fo in zip(dims[:-1], dims[1:]):
+                lim = np.sqrt(6.0 / (fi + fo))
+                ws += [self._rs.uniform(-lim, lim, size=(fi, fo)).astype(np.float32),
+                       np.zeros(fo, np.float32)]
+            self._net.set_weights(ws, model=p)
+        self._last_stats = {}
+
+    # ------------------------------------------------------------------ keras-shaped surface
+    def compile(self, optimizer="adam", loss="binary_crossentropy", metrics=None):
+        if isinstance(optimizer, str):
+            if optimizer.lower() != "adam":
+                raise NotImplementedError("only the Adam optimizer has a fused training kernel")
+            optimizer = Adam()
+        final = self.acts[-1]
+        from_logits = isinstance(loss, BinaryCrossentropy) and loss.from_logits
+        if not (isinstance(loss, BinaryCrossentropy) or loss == "binary_crossentropy"):
+            raise NotImplementedError("only binary cross-entropy is on the BORE path")
+        if from_logits != (final == "linear"):
+            raise NotImplementedError("sigmoid output + 'binary_crossentropy', or linear output + "
+                                      "BinaryCrossentropy(from_logits=True)")
+        self._net.set_optimizer(optimizer.learning_rate, optimizer.beta_1, optimizer.beta_2,
+                                optimizer.epsilon)
+        l2 = []
+        for lyr in self.layers:
+            for r in (lyr.kernel_regularizer, lyr.bias_regularizer):
+                l2.append(0.0 if r is None else float(r.l2))
+        self._net.set_regularizers(l2)
+        self._compiled = True
+
+    def set_weights(self, weights_per_problem):
+        assert len(weights_per_problem) == self.n_problems
+        for p, ws in enumerate(weights_per_problem):
+            self._net.set_weights(ws, model=p)
+
+    def get_weights(self):
+        return [self._net.get_weights(model=p) for p in range(self.n_problems)]
+
+    def fit(self, x, y, batch_size=32, epochs=1, permutations=None, shuffle=True, verbose=0):
+        """x (M, N, D), y (M, N): every problem trains on its own N observations, all in one
+        launch.  ``permutations``: (epochs, N) shared by all problems or (M, epochs, N).
+        Returns the per-problem history loss, shape (M, epochs)."""
+        if not self._compiled:
+            raise RuntimeError("You must compile your model before training/testing.")
+        X = np.asarray(x)
+        z = np.asarray(y)
+        M, N, D = X.shape
+        assert M == self.n_problems and z.shape == (M, N) and D == self.dims[0]
+        if permutations is None:
+            if shuffle:
+                permutations = np.stack([np.stack([self._rs.permutation(N) for _ in range(epochs)])
+                                         for _ in range(M)])
+            else:
+                permutations = np.tile(np.arange(N), (epochs, 1))
+        perm = np.ascontiguousarray(permutations, np.int32)
+        shared_perm = perm.ndim == 2
+        assert perm.shape == ((epochs, N) if shared_perm else (M, epochs, N))
+        net = self._net
+        loss = net.fit_dev(net.to_device(X.reshape(M * N, D), np.float32),
+                           net.to_device(z.reshape(-1).astype(np.float32), np.float32),
+                           N, int(batch_size), int(epochs), net.to_device(perm, np.int32),
+                           model0=0, count=M, shared_data=False, shared_perm=shared_perm)
+        out = loss.cpu().numpy()
+        if verbose:
+            print(f"fit: {M} problems x {epochs} epochs, mean loss {out[:, 0].mean():.4f} -> "
+                  f"{out[:, -1].mean():.4f}")
+        return out
+
+    def predict(self, x):
+        X = np.asarray(x)
+        M, P, D = X.shape
+        assert M == self.n_problems
+        out = self._net.predict_multi_dev(self._net.to_device(X, np.float32))
+        return out.cpu().numpy().reshape(M, P, 1)
+
+    # ------------------------------------------------------------------ argmax per problem
+    def argmax(self, bounds, num_starts=5, num_samples=1024, method="L-BFGS-B",
+               options=dict(maxiter=1000, ftol=1e-9), random_state=None, X_init=None):
+        """One ``OptimizeResult`` (or None) per problem: bore/mixins.py:22-89 for each of them.
+        ``random_state`` draws the (M, num_samples, D) screening samples problem after problem
+        (what M sequential ``argmax`` calls sharing one RandomState would consume); ``X_init``
+        overrides the draw."""
+        import torch
+        assert num_samples >= num_starts > 0
+        if method != "L-BFGS-B":
+            raise NotImplementedError("only L-BFGS-B has a device path")
+        (low, high), dim = from_bounds(bounds)
+        low, high = np.asarray(low, np.float64), np.asarray(high, np.float64)
+        assert dim == self.dims[0]
+        M, net = self.n_problems, self._net
+        if X_init is None:
+            rs = check_random_state(random_state)
+            X_init = rs.uniform(low=low, high=high, size=(M, num_samples, dim))
+        X_init = np.asarray(X_init, np.float64)
+        assert X_init.shape == (M, num_samples, dim)
+        X64 = net.to_device(X_init, np.float64)
+        z_init = net.predict_multi_dev(X64.to(torch.float32))
+        if num_starts < num_samples:
+            ind = net.topk_groups(z_init, num_starts, negate=True)     # (M, k) within-problem
+            X0 = torch.gather(X64, 1, ind.to(torch.int64).unsqueeze(-1).expand(-1, -1, dim)).contiguous()
+        else:
+            X0 = X64
+        opts = dict(options or {})
+        res = net.lbfgsb_multi_dev(X0, low, high, transform=self._transform,
+                                   m=opts.get("maxcor", 10), ftol=opts.get("ftol", 2.2204460492503131e-09),
+                                   gtol=opts.get("gtol", 1e-5), maxiter=opts.get("maxiter", 15000),
+                                   maxfun=opts.get("maxfun", 15000), maxls=opts.get("maxls", 20))
+        keys = net.select_best_groups(res["fun"], res["status"])
+        self._last_stats = dict(evals=res["evals"], rounds=res["rounds"], num_starts=num_starts)
+        # one small record per problem leaves the GPU
+        win = (0x7fffffff - (keys & 0x7fffffff)).clamp(0, num_starts - 1)
+        pick = lambda t: torch.gather(t, 1, win.unsqueeze(-1)).squeeze(-1)
+        xw = torch.gather(res["x"], 1, win.view(M, 1, 1).expand(-1, 1, dim)).squeeze(1)
+        rec = torch.cat([xw, pick(res["fun"]).unsqueeze(-1)] +
+                        [pick(res[k]).to(torch.float64).unsqueeze(-1) for k in ("nit", "nfev", "status", "task")] +
+                        [keys.to(torch.float64).unsqueeze(-1)], dim=1).cpu().numpy()
+        out = []
+        for p in range(M):
+            r = rec[p]
+            if r[dim + 5] == 0:
+                out.append(None)
+                continue
+            st, task = int(r[dim + 3]), int(r[dim + 4])
+            out.append(OptimizeResult(x=r[:dim].copy(), fun=np.float32(r[dim]), nit=int(r[dim + 1]),
+                                      nfev=int(r[dim + 2]), njev=int(r[dim + 2]), status=st,
+                                      success=bool(st == 0), message=lbfgsb_message(st, task)))
+        return out

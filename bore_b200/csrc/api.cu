@@ -184,6 +184,18 @@ int bore_mlp_predict(bore_mlp *h, int model, const float *X_dev, int S, float *o
                          nullptr, nullptr, (cudaStream_t)stream);
 }
 
+int bore_mlp_predict_multi(bore_mlp *h, int model0, int n_models, const float *X_dev,
+                           int points_per_model, float *out_dev, void *stream) {
+  BORE_CHECK(h != nullptr, "NULL handle");
+  BORE_CHECK(model0 >= 0 && n_models >= 1 && model0 + n_models <= h->n_models,
+             "bore_mlp_predict_multi: models [%d,%d) outside [0,%d)", model0, model0 + n_models,
+             h->n_models);
+  BORE_CHECK(points_per_model >= 1 && X_dev && out_dev, "bore_mlp_predict_multi: bad arguments");
+  BORE_CUDA(cudaSetDevice(h->device));
+  return launch_mlp_eval_multi(h, model0, n_models, points_per_model, false, BORE_TRANSFORM_IDENTITY, 0,
+                               X_dev, out_dev, nullptr, nullptr, (cudaStream_t)stream);
+}
+
 int bore_mlp_value_and_grad(bore_mlp *h, int model, int transform, int negate, const float *X_dev,
                             int S, float *f_dev, float *g_dev, void *stream) {
   CHECK_MODEL(h, model);

@@ -62,3 +62,8 @@ static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 int launch_mlp_eval(const bore_mlp *h, int model, bool want_grad, int transform, int negate,
                     const float *X, int S, float *f, float *g, const int *list,
                     const int *n_dev, cudaStream_t stream);
+// batched problems (BASELINE.json configs[3]): one CTA per model; model model0+b owns points
+// [b*per_model, (b+1)*per_model) of X / f / g; `flags` (may be NULL) selects the points to do.
+int launch_mlp_eval_multi(const bore_mlp *h, int model0, int n_models, int per_model, bool want_grad,
+                          int transform, int negate, const float *X, float *f, float *g,
+                          const int *flags, cudaStream_t stream);

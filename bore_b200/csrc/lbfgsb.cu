@@ -50,7 +50,7 @@ static_assert(sizeof(LbScal) <= SCAL_BYTES, "LbScal grew past its slot");
 
 struct LbLayout {
   // offsets in bytes from the workspace base
-  size_t lo, hi, nbd, cnt, evals, lists, xf, f, g, blocks, block_stride, total;
+  size_t lo, hi, nbd, cnt, evals, lists, xf, f, g, pend, blocks, block_stride, total;
 };
 
 __host__ __device__ inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
@@ -67,6 +67,7 @@ inline LbLayout make_layout(int S, int n, int m) {
   L.xf = o; o += align_up((size_t)S * n * sizeof(float), 16);
   L.f = o; o += align_up((size_t)S * sizeof(float), 16);
   L.g = o; o += align_up((size_t)S * n * sizeof(float), 16);
+  L.pend = o; o += align_up((size_t)S * sizeof(int), 16);
   o = align_up(o, 256);
   L.block_stride = align_up(SCAL_BYTES + ((size_t)4 * n + (size_t)n * LB_LDW(m) +
                                           LB_NPERSIST_MM * m * m) * sizeof(double), 128);
@@ -412,14 +413,17 @@ size_t bore_lbfgsb_workspace_bytes(int S, int D, int m) {
   return EXT_HDR + make_layout(S, D, m).total;
 }
 
-int bore_lbfgsb_minimize(bore_mlp *h, int model, int transform, const double *X0_dev, int S,
-                         const double *lo_host, const double *hi_host, int m, double ftol,
-                         double gtol, int maxiter, int maxfun, int maxls, void *work_dev,
-                         size_t work_bytes, double *x_dev, double *fun_dev, int32_t *nit_dev,
-                         int32_t *nfev_dev, int32_t *status_dev, int32_t *task_dev, int *rounds_out,
-                         long long *evals_out, void *stream_) {
+// shared body of bore_lbfgsb_minimize (n_models == 1, per_model == 0: all S starts belong to
+// `model`) and bore_lbfgsb_minimize_multi (start i belongs to model model + i / per_model)
+static int minimize_impl(bore_mlp *h, int model, int n_models, int per_model, int transform,
+                         const double *X0_dev, int S, const double *lo_host, const double *hi_host,
+                         int m, double ftol, double gtol, int maxiter, int maxfun, int maxls,
+                         void *work_dev, size_t work_bytes, double *x_dev, double *fun_dev,
+                         int32_t *nit_dev, int32_t *nfev_dev, int32_t *status_dev, int32_t *task_dev,
+                         int *rounds_out, long long *evals_out, void *stream_) {
   BORE_CHECK(h != nullptr, "NULL handle");
-  BORE_CHECK(model >= 0 && model < h->n_models, "model index %d outside [0,%d)", model, h->n_models);
+  BORE_CHECK(model >= 0 && n_models >= 1 && model + n_models <= h->n_models,
+             "models [%d,%d) outside [0,%d)", model, model + n_models, h->n_models);
   const int n = h->desc.dims[0];
   if (check_opts(S, n, m, maxls)) return -1;
   BORE_CHECK(transform >= 0 && transform <= BORE_TRANSFORM_EXP, "unknown transform code %d", transform);
@@ -438,7 +442,8 @@ int bore_lbfgsb_minimize(bore_mlp *h, int model, int transform, const double *X0
   float *F = reinterpret_cast<float *>(work + L.f);
   float *G = reinterpret_cast<float *>(work + L.g);
   D.F = F; D.G = G;
-  D.pend = nullptr;
+  // batched problems: K2 finds each model's pending starts through per-start flags
+  D.pend = per_model > 0 ? reinterpret_cast<int *>(work + L.pend) : nullptr;
   StepLaunch SL;
   if (plan_step(S, n, m, h->sm_count, SL)) return -1;
   {
@@ -461,7 +466,11 @@ int bore_lbfgsb_minimize(bore_mlp *h, int model, int transform, const double *X0
     for (int k = 0; k < CHUNK; ++k, ++round) {
       const int *list = D.lists + (size_t)(round & 1) * S;
       if (g_prof.enabled) cudaEventRecord(g_prof.get(3 * (size_t)round), stream);
-      rc = launch_mlp_eval(h, model, true, transform, 1, D.xf, S, F, G, list, D.cnt + round % 3, stream);
+      rc = per_model > 0
+               ? launch_mlp_eval_multi(h, model, n_models, per_model, true, transform, 1, D.xf, F, G,
+                                       D.pend, stream)
+               : launch_mlp_eval(h, model, true, transform, 1, D.xf, S, F, G, list, D.cnt + round % 3,
+                                 stream);
       if (rc) break;
       if (g_prof.enabled) cudaEventRecord(g_prof.get(3 * (size_t)round + 1), stream);
       rc = launch_round<float>(D, SL, round, stream);
@@ -514,6 +523,34 @@ int bore_lbfgsb_minimize(bore_mlp *h, int model, int transform, const double *X0
   cudaEventDestroy(ev[1]);
   cudaFreeHost(cnt_host);
   return rc;
+}
+
+int bore_lbfgsb_minimize(bore_mlp *h, int model, int transform, const double *X0_dev, int S,
+                         const double *lo_host, const double *hi_host, int m, double ftol,
+                         double gtol, int maxiter, int maxfun, int maxls, void *work_dev,
+                         size_t work_bytes, double *x_dev, double *fun_dev, int32_t *nit_dev,
+                         int32_t *nfev_dev, int32_t *status_dev, int32_t *task_dev, int *rounds_out,
+                         long long *evals_out, void *stream_) {
+  return minimize_impl(h, model, 1, 0, transform, X0_dev, S, lo_host, hi_host, m, ftol, gtol, maxiter,
+                       maxfun, maxls, work_dev, work_bytes, x_dev, fun_dev, nit_dev, nfev_dev,
+                       status_dev, task_dev, rounds_out, evals_out, stream_);
+}
+
+int bore_lbfgsb_minimize_multi(bore_mlp *h, int model0, int n_models, int starts_per_model,
+                               int transform, const double *X0_dev, const double *lo_host,
+                               const double *hi_host, int m, double ftol, double gtol, int maxiter,
+                               int maxfun, int maxls, void *work_dev, size_t work_bytes,
+                               double *x_dev, double *fun_dev, int32_t *nit_dev, int32_t *nfev_dev,
+                               int32_t *status_dev, int32_t *task_dev, int *rounds_out,
+                               long long *evals_out, void *stream_) {
+  BORE_CHECK(starts_per_model >= 1 && starts_per_model <= 4096,
+             "bore_lbfgsb_minimize_multi: starts_per_model=%d outside [1,4096]", starts_per_model);
+  BORE_CHECK(n_models >= 1 && (long long)n_models * starts_per_model <= 0x7fffffffLL,
+             "bore_lbfgsb_minimize_multi: n_models=%d", n_models);
+  return minimize_impl(h, model0, n_models, starts_per_model, transform, X0_dev,
+                       n_models * starts_per_model, lo_host, hi_host, m, ftol, gtol, maxiter, maxfun,
+                       maxls, work_dev, work_bytes, x_dev, fun_dev, nit_dev, nfev_dev, status_dev,
+                       task_dev, rounds_out, evals_out, stream_);
 }
 
 // per-kernel timing of the NEXT bore_lbfgsb_minimize calls (bench.py's roofline leg)

@@ -21,6 +21,8 @@
 // chunks) for hidden widths <= 32, and 16 unit-groups x 2 point-groups (tiles of 8 points,
 // 64-unit chunks) for wider layers -- the per-warp strip is half as large there, which doubles
 // the warps that fit beside the weights in shared memory.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -114,16 +116,55 @@ __global__ void __launch_bounds__(512)
 mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ params,
                 const float *__restrict__ X,
                 int S, const int *__restrict__ n_dev, const int *__restrict__ list,
-                float *__restrict__ f_out, float *__restrict__ g_out, int transform, float sign) {
+                float *__restrict__ f_out, float *__restrict__ g_out, int transform, float sign,
+                int per_model, const int *__restrict__ flags) {
   extern __shared__ __align__(16) float smem[];
   using M = Map<UGB>;
   constexpr int TP = M::TP, AST = M::AST, CH = M::CH, UG = M::UG;
   const int G = d.n_layers - 1;
   const int tid = threadIdx.x, nthr = blockDim.x;
-  // CTAs with no tile leave before paying for the weight staging: late L-BFGS-B rounds have
-  // few active starts, and the launch is sized for all S of them
-  const int n = n_dev ? min(*n_dev, S) : S;
-  if (blockIdx.x * (nthr >> 5) * TP >= n) return;
+  // Two addressing modes.  Single model (per_model == 0): the launch covers S points (or the
+  // first *n_dev of `list`), tiles are dealt round-robin to all warps of the grid.  Batched
+  // problems (per_model > 0): CTA b works for model b on points [b*per_model, (b+1)*per_model),
+  // of which only those with flags[point] != 0 are evaluated (flags == NULL: all of them).
+  const bool multi = per_model > 0;
+  int n, tile0, tile_step;
+  long row_base = 0;
+  int *llist = reinterpret_cast<int *>(smem + P.weights_total + (nthr >> 5) * P.warp_total);
+  if (multi) {
+    params += (size_t)blockIdx.x * d.n_params;
+    row_base = (long)blockIdx.x * per_model;
+    if (flags) {  // order-preserving compaction of this model's pending starts
+      __shared__ int s_cnt;
+      if (tid == 0) s_cnt = 0;
+      __syncthreads();
+      for (int c0 = 0; c0 < per_model; c0 += nthr) {
+        const int i = c0 + tid;
+        const bool on = i < per_model && flags[row_base + i] != 0;
+        const unsigned b = __ballot_sync(0xffffffffu, on);
+        int wbase = 0;
+        if ((tid & 31) == 0 && b) wbase = atomicAdd(&s_cnt, __popc(b));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (on) llist[wbase + __popc(b & ((1u << (tid & 31)) - 1u))] = i;
+      }
+      __syncthreads();
+      n = s_cnt;
+      list = llist;
+    } else {
+      n = per_model;
+      list = nullptr;
+    }
+    if (n == 0) return;
+    tile0 = 0;
+    tile_step = nthr >> 5;
+  } else {
+    // CTAs with no tile leave before paying for the weight staging: late L-BFGS-B rounds have
+    // few active starts, and the launch is sized for all S of them
+    n = n_dev ? min(*n_dev, S) : S;
+    if (blockIdx.x * (nthr >> 5) * TP >= n) return;
+    tile0 = blockIdx.x * (nthr >> 5);
+    tile_step = gridDim.x * (nthr >> 5);
+  }
 
   // ---- stage weights (zero padded) ----
   for (int l = 0; l < G; ++l) {
@@ -162,7 +203,7 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
   const int D = d.dims[0];
   const float *wl = smem + P.wl;
 
-  for (int tile = blockIdx.x * nwarps + warp; tile < n_tiles; tile += gridDim.x * nwarps) {
+  for (int tile = tile0 + warp; tile < n_tiles; tile += tile_step) {
     const int p0 = tile * TP;
     // ---- load the 16 input rows, transposed into buf0[k][p] ----
     {
@@ -171,7 +212,7 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
       for (int pl = 0; pl < TP; ++pl) {
         const int idx = p0 + pl;
         const bool ok = idx < n;
-        const long row = ok ? (list ? list[idx] : idx) : 0;
+        const long row = ok ? row_base + (list ? list[idx] : idx) : 0;
         for (int k = lane; k < rows0; k += 32)
           xb[k * AST + pl] = (ok && k < D) ? X[row * D + k] : 0.f;
       }
@@ -242,7 +283,7 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
         fval = u;
       }
       const int idx = p0 + pg * 4 + i;
-      if (ug == 0 && idx < n) f_out[list ? list[idx] : idx] = fval;
+      if (ug == 0 && idx < n) f_out[row_base + (list ? list[idx] : idx)] = fval;
     }
     if (!GRAD) { __syncwarp(); continue; }
 
@@ -254,7 +295,7 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int idx = p0 + pg * 4 + i;
-          if (idx < n) g_out[(long)(list ? list[idx] : idx) * D + k] = dpre[i] * w;
+          if (idx < n) g_out[(row_base + (list ? list[idx] : idx)) * D + k] = dpre[i] * w;
         }
       }
       __syncwarp();
@@ -312,7 +353,7 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
         for (int pl = 0; pl < TP; ++pl) {
           const int idx = p0 + pl;
           if (idx >= n) break;
-          const long row = list ? list[idx] : idx;
+          const long row = row_base + (list ? list[idx] : idx);
           for (int k = lane; k < D; k += 32) g_out[row * D + k] = Hin[k * AST + pl];
         }
         __syncwarp();
@@ -326,48 +367,74 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
 template <bool GRAD, int UGB>
 static int launch_variant(const bore_mlp *h, const MlpDesc &d, const float *params, const float *X,
                           int S, float *f, float *g, const int *list, const int *n_dev,
-                          int transform, float sign, cudaStream_t stream) {
+                          int transform, float sign, int n_models, int per_model, const int *flags,
+                          cudaStream_t stream) {
   using M = Map<UGB>;
   SmemPlan P;
   make_plan(d, GRAD, M::CH, M::AST, P);
   const int max_smem = 227 * 1024;
-  // warps per CTA: as many as fit (<= 16), at least 1
+  const bool multi = per_model > 0;
+  const size_t list_bytes = (multi && flags) ? (size_t)per_model * sizeof(int) : 0;
+  // warps per CTA: as many as fit (<= 16) -- in batched mode no more than the model has tiles
   int warps = 16;
-  while (warps > 1 &&
-         (size_t)(P.weights_total + warps * P.warp_total) * sizeof(float) > (size_t)max_smem)
+  if (multi) warps = std::min(16, std::max(1, (per_model + M::TP - 1) / M::TP));
+  while (warps > 1 && (size_t)(P.weights_total + warps * P.warp_total) * sizeof(float) + list_bytes + 16 >
+                          (size_t)max_smem)
     --warps;
-  const size_t smem = (size_t)(P.weights_total + warps * P.warp_total) * sizeof(float);
-  BORE_CHECK(smem <= (size_t)max_smem, "mlp_eval: model needs %zu B of shared memory (> %d)",
+  const size_t smem = (size_t)(P.weights_total + warps * P.warp_total) * sizeof(float) + list_bytes;
+  BORE_CHECK(smem + 16 <= (size_t)max_smem, "mlp_eval: model needs %zu B of shared memory (> %d)",
              smem, max_smem);
-  const int n_tiles = (S + M::TP - 1) / M::TP;
-  int ctas_needed = (n_tiles + warps - 1) / warps;
-  int per_sm = (int)((size_t)max_smem / (smem + 1024));
-  if (per_sm < 1) per_sm = 1;
-  if (per_sm * warps > 48) per_sm = 48 / warps > 0 ? 48 / warps : 1;
-  int grid = h->sm_count * per_sm;
-  if (grid > ctas_needed) grid = ctas_needed;
-  if (grid < 1) grid = 1;
+  int grid;
+  if (multi) {
+    grid = n_models;
+  } else {
+    const int n_tiles = (S + M::TP - 1) / M::TP;
+    int ctas_needed = (n_tiles + warps - 1) / warps;
+    int per_sm = (int)((size_t)max_smem / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm * warps > 48) per_sm = 48 / warps > 0 ? 48 / warps : 1;
+    grid = h->sm_count * per_sm;
+    if (grid > ctas_needed) grid = ctas_needed;
+    if (grid < 1) grid = 1;
+  }
   BORE_CUDA(cudaFuncSetAttribute(mlp_eval_kernel<GRAD, UGB>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   mlp_eval_kernel<GRAD, UGB><<<grid, warps * 32, smem, stream>>>(d, P, params, X, S, n_dev, list, f, g,
-                                                               transform, sign);
+                                                               transform, sign, per_model, flags);
   BORE_CUDA(cudaGetLastError());
   return 0;
+}
+
+static int dispatch(const bore_mlp *h, const float *params, bool want_grad, int transform,
+                    int negate, const float *X, int S, float *f, float *g, const int *list,
+                    const int *n_dev, int n_models, int per_model, const int *flags,
+                    cudaStream_t stream) {
+  const MlpDesc &d = h->desc;
+  int widest = 0;
+  for (int l = 1; l < d.n_layers; ++l) widest = d.dims[l] > widest ? d.dims[l] : widest;
+  const bool wide = widest > 32;  // 64-unit chunks, tiles of 8 points
+  const float sign = negate ? -1.f : 1.f;
+#define BORE_EVAL(G_, U_) \
+  launch_variant<G_, U_>(h, d, params, X, S, f, g, list, n_dev, transform, sign, n_models, per_model, flags, stream)
+  if (want_grad) return wide ? BORE_EVAL(true, 4) : BORE_EVAL(true, 3);
+  return wide ? BORE_EVAL(false, 4) : BORE_EVAL(false, 3);
+#undef BORE_EVAL
 }
 
 int launch_mlp_eval(const bore_mlp *h, int model, bool want_grad, int transform, int negate,
                     const float *X, int S, float *f, float *g, const int *list,
                     const int *n_dev, cudaStream_t stream) {
   if (S <= 0) return 0;
-  const MlpDesc &d = h->desc;
-  int widest = 0;
-  for (int l = 1; l < d.n_layers; ++l) widest = d.dims[l] > widest ? d.dims[l] : widest;
-  const bool wide = widest > 32;  // 64-unit chunks, tiles of 8 points
-  const float *params = h->params + (size_t)model * d.n_params;
-  const float sign = negate ? -1.f : 1.f;
-  if (want_grad)
-    return wide ? launch_variant<true, 4>(h, d, params, X, S, f, g, list, n_dev, transform, sign, stream)
-                : launch_variant<true, 3>(h, d, params, X, S, f, g, list, n_dev, transform, sign, stream);
-  return wide ? launch_variant<false, 4>(h, d, params, X, S, f, g, list, n_dev, transform, sign, stream)
-              : launch_variant<false, 3>(h, d, params, X, S, f, g, list, n_dev, transform, sign, stream);
+  return dispatch(h, h->params + (size_t)model * h->desc.n_params, want_grad, transform, negate, X, S,
+                  f, g, list, n_dev, 1, 0, nullptr, stream);
+}
+
+// batched problems: model model0+b evaluates points [b*per_model, (b+1)*per_model) of X (those
+// with flags != 0 when `flags` is given), one CTA per model
+int launch_mlp_eval_multi(const bore_mlp *h, int model0, int n_models, int per_model, bool want_grad,
+                          int transform, int negate, const float *X, float *f, float *g,
+                          const int *flags, cudaStream_t stream) {
+  if (n_models <= 0 || per_model <= 0) return 0;
+  return dispatch(h, h->params + (size_t)model0 * h->desc.n_params, want_grad, transform, negate, X,
+                  n_models * per_model, f, g, nullptr, nullptr, n_models, per_model, flags, stream);
 }

@@ -97,6 +97,63 @@ select_best_kernel(const double *__restrict__ fun, const int32_t *__restrict__ s
   if ((threadIdx.x & 31) == 0 && best) atomicMax(key_out, best);
 }
 
+// ---- grouped variants (batched problems: one group of samples / starts per model) ----
+// k smallest of each group of P values: one CTA per group, keys sorted in shared memory
+__global__ void __launch_bounds__(1024)
+topk_groups_kernel(const float *__restrict__ f, int P, int n_pow2, int k, float sign,
+                   int32_t *__restrict__ idx) {
+  extern __shared__ unsigned long long sk[];
+  const float *fg = f + (size_t)blockIdx.x * P;
+  for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+    unsigned long long key = ~0ULL;
+    if (i < P) {
+      const float v = sign * fg[i];
+      const unsigned o = (v != v) ? 0xffffffffu : orderable(v);
+      key = ((unsigned long long)o << 32) | (unsigned)i;
+    }
+    sk[i] = key;
+  }
+  __syncthreads();
+  for (int kk = 2; kk <= n_pow2; kk <<= 1)
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = sk[i], b = sk[ixj];
+          const bool up = (i & kk) == 0;
+          if ((a > b) == up) { sk[i] = b; sk[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < k; i += blockDim.x)
+    idx[(size_t)blockIdx.x * k + i] = (int32_t)(sk[i] & 0xffffffffu);
+}
+
+// first minimum of every group of `per_group` results: one warp per group
+__global__ void __launch_bounds__(128)
+select_best_groups_kernel(const double *__restrict__ fun, const int32_t *__restrict__ status,
+                          int n_groups, int per_group, unsigned long long *__restrict__ keys) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (g >= n_groups) return;
+  unsigned long long best = 0ULL;
+  for (int i = lane; i < per_group; i += 32) {
+    const size_t q = (size_t)g * per_group + i;
+    const int st = status[q];
+    if (!(st == 0 || st == 1)) continue;
+    const float v = (float)fun[q];
+    if (v != v) continue;
+    const unsigned long long key = ((unsigned long long)orderable(-v) << 31) |
+                                   (unsigned long long)(0x7fffffffLL - i);
+    best = key > best ? key : best;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+    best = other > best ? other : best;
+  }
+  if (lane == 0) keys[g] = best;
+}
+
 int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 }  // namespace
@@ -155,6 +212,33 @@ int bore_select_best(const double *fun_dev, const int32_t *status_dev, const uin
         reinterpret_cast<unsigned long long *>(key_dev));
     BORE_CUDA(cudaGetLastError());
   }
+  return 0;
+}
+
+int bore_topk_smallest_groups(const float *f_dev, int n_groups, int per_group, int k, int negate,
+                              int32_t *idx_dev, int device, void *stream_) {
+  BORE_CHECK(n_groups >= 1 && per_group >= 1 && k >= 1 && k <= per_group,
+             "bore_topk_smallest_groups: n_groups=%d per_group=%d k=%d", n_groups, per_group, k);
+  BORE_CHECK(per_group <= 4096, "bore_topk_smallest_groups: at most 4096 samples per group");
+  BORE_CHECK(f_dev && idx_dev, "bore_topk_smallest_groups: NULL buffer");
+  BORE_CHECK(bore_device_count() > 0, "no CUDA device visible -- bore_b200 has no CPU fallback");
+  BORE_CUDA(cudaSetDevice(device));
+  const int n = next_pow2(per_group);
+  topk_groups_kernel<<<n_groups, std::min(1024, std::max(32, n / 2)), (size_t)n * sizeof(unsigned long long),
+                       (cudaStream_t)stream_>>>(f_dev, per_group, n, k, negate ? -1.f : 1.f, idx_dev);
+  BORE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bore_select_best_groups(const double *fun_dev, const int32_t *status_dev, int n_groups,
+                            int per_group, int64_t *keys_dev, int device, void *stream_) {
+  BORE_CHECK(n_groups >= 1 && per_group >= 1 && fun_dev && status_dev && keys_dev,
+             "bore_select_best_groups: bad arguments");
+  BORE_CHECK(bore_device_count() > 0, "no CUDA device visible -- bore_b200 has no CPU fallback");
+  BORE_CUDA(cudaSetDevice(device));
+  select_best_groups_kernel<<<(n_groups * 32 + 127) / 128, 128, 0, (cudaStream_t)stream_>>>(
+      fun_dev, status_dev, n_groups, per_group, reinterpret_cast<unsigned long long *>(keys_dev));
+  BORE_CUDA(cudaGetLastError());
   return 0;
 }
 

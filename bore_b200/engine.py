@@ -268,6 +268,62 @@ class NativeMLP:
                                              int(idx_offset), _ptr(key), self.device, self._stream()))
         return key
 
+    # ------------------------------------------------------------------ batched problems
+    def predict_multi_dev(self, X_dev, model0=0):
+        """X_dev (M, P, D) float32 -> (M, P) float32, model model0+b on block b."""
+        torch = _torch()
+        M, P, D = X_dev.shape
+        assert D == self.D and X_dev.dtype == torch.float32 and X_dev.is_contiguous()
+        out = torch.empty(M, P, dtype=torch.float32, device=self._tdev())
+        _lib.check(self.lib.bore_mlp_predict_multi(self.h, int(model0), int(M), _ptr(X_dev), int(P),
+                                                   _ptr(out), self._stream()))
+        return out
+
+    def topk_groups(self, f_dev, k, negate=False):
+        """Per row of f_dev (M, P): indices of the k smallest (of -f when negate), ascending."""
+        torch = _torch()
+        M, P = f_dev.shape
+        assert f_dev.dtype == torch.float32 and f_dev.is_contiguous()
+        idx = torch.empty(M, int(k), dtype=torch.int32, device=self._tdev())
+        _lib.check(self.lib.bore_topk_smallest_groups(_ptr(f_dev), int(M), int(P), int(k),
+                                                      1 if negate else 0, _ptr(idx), self.device,
+                                                      self._stream()))
+        return idx
+
+    def lbfgsb_multi_dev(self, X0_dev, lo, hi, transform="identity", m=10, ftol=1e-9, gtol=1e-5,
+                         maxiter=1000, maxfun=15000, maxls=20, model0=0):
+        """X0_dev (M, K, D) float64: K starts for each of M models, all advanced together."""
+        torch = _torch()
+        M, K, D = X0_dev.shape
+        assert D == self.D and X0_dev.dtype == torch.float64 and X0_dev.is_contiguous()
+        S = M * K
+        lo = np.ascontiguousarray(np.broadcast_to(np.asarray(lo, np.float64), (D,)))
+        hi = np.ascontiguousarray(np.broadcast_to(np.asarray(hi, np.float64), (D,)))
+        work = self._workspace(self.lib.bore_lbfgsb_workspace_bytes(S, D, m))
+        dev = self._tdev()
+        x = torch.empty(M, K, D, dtype=torch.float64, device=dev)
+        fun = torch.empty(M, K, dtype=torch.float64, device=dev)
+        ints = torch.empty(4, M, K, dtype=torch.int32, device=dev)
+        rounds, evals = C.c_int(), C.c_longlong()
+        _lib.check(self.lib.bore_lbfgsb_minimize_multi(
+            self.h, int(model0), int(M), int(K), TRANSFORM_CODES[transform], _ptr(X0_dev),
+            _np_ptr(lo), _np_ptr(hi), int(m), float(ftol), float(gtol), int(maxiter), int(maxfun),
+            int(maxls), _ptr(work), work.numel(), _ptr(x), _ptr(fun), _ptr(ints[0]), _ptr(ints[1]),
+            _ptr(ints[2]), _ptr(ints[3]), C.byref(rounds), C.byref(evals), self._stream()))
+        return dict(x=x, fun=fun, nit=ints[0], nfev=ints[1], status=ints[2], task=ints[3],
+                    rounds=rounds.value, evals=evals.value)
+
+    def select_best_groups(self, fun_dev, status_dev):
+        """(M, K) results -> int64 (M,) keys; key & 0x7fffffff = 0x7fffffff - winner's index in
+        its group, key 0 = no start of the group qualifies."""
+        torch = _torch()
+        M, K = fun_dev.shape
+        assert fun_dev.dtype == torch.float64 and status_dev.dtype == torch.int32
+        keys = torch.empty(M, dtype=torch.int64, device=self._tdev())
+        _lib.check(self.lib.bore_select_best_groups(_ptr(fun_dev), _ptr(status_dev), int(M), int(K),
+                                                    _ptr(keys), self.device, self._stream()))
+        return keys
+
     # ------------------------------------------------------------------ K1
     def fit_dev(self, X_dev, z_dev, N, batch_size, epochs, perm_dev, loss_dev=None,
                 model0=0, count=1, shared_data=True, shared_perm=True):

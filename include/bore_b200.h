@@ -185,6 +185,35 @@ int bore_select_best(const double *fun_dev, const int32_t *status_dev,
                      const uint8_t *keep_dev, int S, int64_t idx_offset, int64_t *key_dev,
                      int device, void *stream);
 
+/* ---- batched problems -----------------------------------------------------------------
+ * BASELINE.json configs[3]: M independent BO problems (seeds / concurrent optimisations /
+ * per-budget classifiers), each the reference's own `fit` + `argmax` (README.rst:93-96), advanced
+ * together.  Training already takes a model range (bore_mlp_fit).  For the argmax, model
+ * model0+b owns points / starts [b*per_model, (b+1)*per_model) of every array below; one CTA
+ * per model evaluates its points, the L-BFGS-B stepper is the same kernel as for one model.
+ *   bore_mlp_predict_multi       keras predict per problem (bore/mixins.py:50)
+ *   bore_topk_smallest_groups    np.argpartition per problem (bore/mixins.py:56): idx_dev
+ *                                [n_groups][k], indices WITHIN the group, ascending value
+ *   bore_lbfgsb_minimize_multi   the scipy loop of bore/mixins.py:57-61 for every problem;
+ *                                arguments as bore_lbfgsb_minimize with S = n_models *
+ *                                starts_per_model
+ *   bore_select_best_groups      the scan of bore/mixins.py:80-87 per problem: keys_dev
+ *                                [n_groups] int64, low 31 bits = 0x7fffffff - index within the
+ *                                group, 0 when no start of the group qualifies               */
+int bore_mlp_predict_multi(bore_mlp *h, int model0, int n_models, const float *X_dev,
+                           int points_per_model, float *out_dev, void *stream);
+int bore_topk_smallest_groups(const float *f_dev, int n_groups, int per_group, int k, int negate,
+                              int32_t *idx_dev, int device, void *stream);
+int bore_lbfgsb_minimize_multi(bore_mlp *h, int model0, int n_models, int starts_per_model,
+                               int transform, const double *X0_dev, const double *lo_host,
+                               const double *hi_host, int m, double ftol, double gtol, int maxiter,
+                               int maxfun, int maxls, void *work_dev, size_t work_bytes,
+                               double *x_dev, double *fun_dev, int32_t *nit_dev, int32_t *nfev_dev,
+                               int32_t *status_dev, int32_t *task_dev, int *rounds_out,
+                               long long *evals_out, void *stream);
+int bore_select_best_groups(const double *fun_dev, const int32_t *status_dev, int n_groups,
+                            int per_group, int64_t *keys_dev, int device, void *stream);
+
 /* ---- measurement helper -----------------------------------------------------------------
  * FP32 FFMA-only microbenchmark (register-resident FMA chains, all SMs): the measured
  * denominator for the FP32 roofline, since MEASURED_PEAKS.json carries only HBM and BF16.
