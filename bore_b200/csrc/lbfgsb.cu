@@ -158,23 +158,35 @@ __global__ void __launch_bounds__(128) lbfgsb_init_kernel(LbDev D, const double 
 }
 
 // ---------------------------------------------------------------- warp variant: one round
-// lazy loader of the limited-memory matrices (state block -> the warp's smem workspace)
+// linear staging copies between a start's persisted block (HBM) and the warp's workspace;
+// real functions so that the kernel holds one copy of each (code size, see lbfgsb_core.h)
+__device__ __noinline__ void lb_g2s(double *dst, const double *__restrict__ src, int cnt) {
+  __builtin_assume(__isShared(dst));
+#pragma unroll 1
+  for (int i = threadIdx.x & 31; i < cnt; i += 32) dst[i] = src[i];
+}
+__device__ __noinline__ void lb_s2g(double *__restrict__ dst, const double *src, int cnt) {
+  __builtin_assume(__isShared(src));
+#pragma unroll 1
+  for (int i = threadIdx.x & 31; i < cnt; i += 32) dst[i] = src[i];
+}
+
+// lazy loader of the limited-memory matrices (state block -> the warp's smem workspace);
+// W | sy ss yy tinv are contiguous in both places
 struct BlockMem {
   const LbParams &P;
   lbw::LbWork &w;
   LbScal &s;
-  double *gW, *gM;  // this start's W and [sy ss yy tinv] in HBM
+  double *gW;  // this start's W, followed by [sy ss yy tinv], in HBM
   bool loaded = false, is_dirty = false, vec_dirty = false;
-  __device__ BlockMem(const LbParams &P_, lbw::LbWork &w_, LbScal &s_, double *gW_, double *gM_)
-      : P(P_), w(w_), s(s_), gW(gW_), gM(gM_) {}
+  __device__ BlockMem(const LbParams &P_, lbw::LbWork &w_, LbScal &s_, double *gW_)
+      : P(P_), w(w_), s(s_), gW(gW_) {}
+  __device__ int count() const { return P.n * LB_LDW(P.m) + LB_NPERSIST_MM * P.m * P.m; }
   __device__ void load() {
     if (loaded) return;
     loaded = true;
     if (s.col == 0) return;  // empty memory: nothing valid to read
-    const int lane = threadIdx.x & 31;
-    const int nW = P.n * LB_LDW(P.m), nM = LB_NPERSIST_MM * P.m * P.m;
-    for (int i = lane; i < nW; i += 32) w.W[i] = gW[i];
-    for (int i = lane; i < nM; i += 32) w.sy[i] = gM[i];  // sy, ss, yy, tinv contiguous
+    lb_g2s(w.W, gW, count());
     __syncwarp();
     lbw::lb_prep_ld(w, P.m, s.col);
   }
@@ -182,13 +194,16 @@ struct BlockMem {
   __device__ void dirty_vec() { vec_dirty = true; }
   __device__ void store() {
     if (!is_dirty) return;
-    const int lane = threadIdx.x & 31;
-    const int nW = P.n * LB_LDW(P.m), nM = LB_NPERSIST_MM * P.m * P.m;
     __syncwarp();
-    for (int i = lane; i < nW; i += 32) gW[i] = w.W[i];
-    for (int i = lane; i < nM; i += 32) gM[i] = w.sy[i];
+    lb_s2g(gW, w.W, count());
   }
 };
+
+// CTA header in dynamic shared memory: the formk output map, then lo / hi / nbd
+__host__ __device__ inline size_t lb_header_bytes(int n) {
+  return align_up(LB_FORMK_ACC * 32 * sizeof(int), 16) + 2 * align_up(n * sizeof(double), 16) +
+         align_up(n * sizeof(int), 16);
+}
 
 template <typename FG>
 __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t warp_bytes) {
@@ -199,64 +214,73 @@ __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t w
   const int cur = round % 3, nxt = (round + 1) % 3, clr = (round + 2) % 3;
   if (blockIdx.x == 0 && threadIdx.x == 0) D.cnt[clr] = 0;
   const int n_active = D.cnt[cur];
+  if (blockIdx.x * wpb >= n_active) return;
   const int *list_cur = D.lists + (size_t)(round & 1) * D.S;
   int *list_nxt = D.lists + (size_t)((round + 1) & 1) * D.S;
 
-  unsigned char *base = smem_raw + warp_bytes * wib;
+  // ---- CTA header: formk map, bounds ----
+  int *ftab = reinterpret_cast<int *>(smem_raw);
+  double *s_lo = reinterpret_cast<double *>(smem_raw + align_up(LB_FORMK_ACC * 32 * sizeof(int), 16));
+  double *s_hi = s_lo + align_up(n * sizeof(double), 16) / sizeof(double);
+  int *s_nbd = reinterpret_cast<int *>(s_hi + align_up(n * sizeof(double), 16) / sizeof(double));
+#pragma unroll 1
+  for (int o = threadIdx.x; o < LB_FORMK_ACC * 32; o += blockDim.x) ftab[o] = lbw::lb_formk_code(o, m);
+#pragma unroll 1
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    s_lo[i] = D.P.lo[i];
+    s_hi[i] = D.P.hi[i];
+    s_nbd[i] = D.P.nbd[i];
+  }
+  __syncthreads();
+  LbParams P = D.P;
+  P.lo = s_lo; P.hi = s_hi; P.nbd = s_nbd;
+
+  unsigned char *base = smem_raw + lb_header_bytes(n) + warp_bytes * wib;
   lbw::LbWork w;
   lbw::lb_carve(w, reinterpret_cast<double *>(base),
                 reinterpret_cast<int *>(base + lbw::lb_work_doubles(n, m) * sizeof(double)), n, m);
+  w.ftab = ftab;
   const FG *F = static_cast<const FG *>(D.F);
   const FG *G = static_cast<const FG *>(D.G);
 
+#pragma unroll 1
   for (int idx = blockIdx.x * wpb + wib; idx < n_active; idx += gridDim.x * wpb) {
     const int sid = list_cur[idx];
     LbScal s = *scal_of(D, sid);
     double *gvec = reinterpret_cast<double *>(D.blocks + D.block_stride * sid + SCAL_BYTES);
-    double *gW = gvec + 4 * n;
-    double *gM = gW + (size_t)n * LB_LDW(m);
     double *xr = D.xreq + (size_t)sid * n;
+    const FG *gr = G + (size_t)sid * n;
 
     s.f = (double)F[sid];
+#pragma unroll 1
     for (int i = lane; i < n; i += 32) {
       w.x[i] = xr[i];
-      w.g[i] = (double)G[(size_t)sid * n + i];
-      w.iwhere[i] = init_iwhere(D.P, i);
+      w.g[i] = (double)gr[i];
+      const int nb = s_nbd[i];
+      w.iwhere[i] = nb == 0 ? -1 : ((nb == 2 && s_hi[i] - s_lo[i] <= 0.0) ? 3 : 0);
     }
-    if (s.phase == LB_PH_LNSRCH) {
-      for (int i = lane; i < n; i += 32) {
-        w.t[i] = gvec[i];
-        w.r[i] = gvec[n + i];
-        w.d[i] = gvec[2 * n + i];
-        w.z[i] = gvec[3 * n + i];
-      }
-    }
+    if (s.phase == LB_PH_LNSRCH) lb_g2s(w.t, gvec, 4 * n);  // t r d z
     __syncwarp();
-    BlockMem mem(D.P, w, s, gW, gM);
+    BlockMem mem(P, w, s, gvec + 4 * n);
     const int col_in = s.col;
     const bool was_ls = s.phase == LB_PH_LNSRCH;
-    const int pend = lbw::lb_advance(D.P, w, s, mem);
+    const int pend = lbw::lb_advance(P, w, s, mem);
     __syncwarp();
     if (lane == 0)
       atomicAdd(D.bytes, step_bytes(n, (int)sizeof(FG), was_ls, mem.loaded, col_in, s.col,
                                     pend != 0, mem.is_dirty));
     if (pend) {
       int changed = 0;
+      float *xf = D.xf ? D.xf + (size_t)sid * n : nullptr;
+#pragma unroll 1
       for (int i = lane; i < n; i += 32) {
         const double xi = w.x[i];
         changed |= (xr[i] != xi);
         xr[i] = xi;
-        if (D.xf) D.xf[(size_t)sid * n + i] = (float)xi;
+        if (xf) xf[i] = (float)xi;
       }
       if (__any_sync(0xffffffffu, changed)) s.nfev += 1;
-      if (mem.vec_dirty) {
-        for (int i = lane; i < n; i += 32) {
-          gvec[i] = w.t[i];
-          gvec[n + i] = w.r[i];
-          gvec[2 * n + i] = w.d[i];
-          gvec[3 * n + i] = w.z[i];
-        }
-      }
+      if (mem.vec_dirty) lb_s2g(gvec, w.t, 4 * n);
       mem.store();
       if (lane == 0) {
         const int pos = atomicAdd(&D.cnt[nxt], 1);
@@ -264,7 +288,7 @@ __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t w
         atomicAdd(D.evals, 1ULL);
       }
     } else {
-      for (int i = lane; i < n; i += 32) xr[i] = w.x[i];  // final iterate
+      lb_s2g(xr, w.x, n);  // final iterate
     }
     if (lane == 0) {
       *scal_of(D, sid) = s;
@@ -314,22 +338,25 @@ struct StepLaunch {
 
 int plan_step(int S, int n, int m, int sm_count, StepLaunch &L) {
   L.warp_bytes = align_up(lbw::lb_work_doubles(n, m) * sizeof(double) + lbw::lb_work_ints(n) * sizeof(int), 16);
-  const size_t max_smem = 227 * 1024;
-  BORE_CHECK(L.warp_bytes <= max_smem, "lbfgsb: n=%d needs %zu B of shared memory per start", n,
-             L.warp_bytes);
-  // warps per CTA: whatever packs the most starts into an SM's shared memory (1 KB per CTA is
-  // reserved by the system); ties go to the larger CTA
+  const size_t hdr = lb_header_bytes(n);
+  const size_t max_block = 227 * 1024, max_sm = 228 * 1024;  // per CTA (opt-in) / per SM
+  BORE_CHECK(L.warp_bytes + hdr <= max_block, "lbfgsb: n=%d needs %zu B of shared memory per start", n,
+             L.warp_bytes + hdr);
+  // warps per CTA: whatever packs the most starts into an SM's shared memory (the CTA header and
+  // the 1 KB the system reserves per CTA are paid once per CTA); ties go to the larger CTA.
+  // 168 registers per thread cap an SM at 12 warps.
   int wpb = 1, best = 0;
-  for (int c = 1; c <= 4; ++c) {
-    if (c * L.warp_bytes > max_smem) break;
-    const int per_sm = (int)(max_smem / (c * L.warp_bytes + 1024)) * c;
-    if (per_sm >= best) { best = per_sm; wpb = c; }
+  for (int c = 1; c <= 12; ++c) {
+    if (c * L.warp_bytes + hdr > max_block) break;
+    int ctas = (int)(max_sm / (c * L.warp_bytes + hdr + 1024));
+    if (ctas * c > 12) ctas = 12 / c;
+    if (ctas * c >= best) { best = ctas * c; wpb = c; }
   }
   L.block = wpb * 32;
-  L.smem = wpb * L.warp_bytes;
-  int per_sm = (int)(max_smem / (L.smem + 1024));
+  L.smem = hdr + wpb * L.warp_bytes;
+  int per_sm = (int)(max_sm / (L.smem + 1024));
+  if (per_sm * wpb > 12) per_sm = 12 / wpb;
   if (per_sm < 1) per_sm = 1;
-  if (per_sm * wpb > 12) per_sm = std::max(1, 12 / wpb);  // 168 registers per thread
   L.grid = sm_count * per_sm;
   const int need = (S + wpb - 1) / wpb;
   if (L.grid > need) L.grid = need;

@@ -38,6 +38,25 @@
 #undef LB_NL
 #undef LB_SYNC
 #undef LB_FOR
+#undef LB_UNROLL1
+#undef LB_NI
+#undef LB_SHARED
+// Code size is a first-order cost on the device: the stepper is ~10^4 mostly-serial
+// instructions per step and every warp of an SM sits at a different place in it, so a kernel
+// that does not fit the instruction caches stalls on instruction fetch (ncu: no_instruction
+// was 55 % of all stall cycles with everything inlined and unrolled, profiles/r01_notes.md).
+// Hence: inner loops stay rolled (LB_UNROLL1), helpers with several call sites are real
+// functions (LB_NI), and their pointer arguments are declared shared (LB_SHARED) so that
+// they still compile to LDS/STS.
+#if LB_VARIANT == 0
+#define LB_UNROLL1
+#define LB_NI inline
+#define LB_SHARED(p) ((void)0)
+#else
+#define LB_UNROLL1 _Pragma("unroll 1")
+#define LB_NI __device__ __noinline__
+#define LB_SHARED(p) __builtin_assume(__isShared(p))
+#endif
 #if LB_VARIANT == 0
 #define LB_FN inline
 #else
@@ -54,26 +73,29 @@
 #define LB_NL 1
 #define LB_SYNC() ((void)0)
 #endif
-#define LB_FOR(i, n) for (int i = LB_LANE; i < (n); i += LB_NL)
+#define LB_FOR(i, n) LB_UNROLL1 for (int i = LB_LANE; i < (n); i += LB_NL)
 
 typedef double *LbDP;
 typedef int *LbIP;
 
 // ------------------------------------------------------------------ warp collectives
-LB_FN double lb_sum(double v) {
+LB_NI double lb_sum(double v) {
 #if LB_WARP
+  LB_UNROLL1
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
 #endif
   return v;
 }
-LB_FN double lb_max(double v) {
+LB_NI double lb_max(double v) {
 #if LB_WARP
+  LB_UNROLL1
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
 #endif
   return v;
 }
-LB_FN int lb_isum(int v) {
+LB_NI int lb_isum(int v) {
 #if LB_WARP
+  LB_UNROLL1
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
 #endif
   return v;
@@ -86,14 +108,19 @@ LB_FN int lb_any(int p) {
 #endif
 }
 // minimum value and the SMALLEST index attaining it
-LB_FN void lb_argmin(double &v, int &idx) {
+struct LbArgMin { double v; int idx; };
+LB_NI LbArgMin lb_argmin(double v, int idx) {
 #if LB_WARP
+  LB_UNROLL1
   for (int o = 16; o > 0; o >>= 1) {
     double ov = __shfl_xor_sync(0xffffffffu, v, o);
     int oi = __shfl_xor_sync(0xffffffffu, idx, o);
     if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
   }
 #endif
+  LbArgMin r;
+  r.v = v; r.idx = idx;
+  return r;
 }
 
 // scratch + state views for one start (all in fast memory while a step runs)
@@ -118,6 +145,7 @@ struct LbWork {
   LbIP iwhere;                        // [n]
   LbIP index;                         // [n] free variables first (count nfree), active after
                                       //     (warp variant only; the serial variants mask)
+  const int *ftab;                    // formk output map (lb_formk_code), one per CTA, warp variant only
 };
 
 LB_HD size_t lb_work_doubles(int n, int m) {
@@ -126,9 +154,11 @@ LB_HD size_t lb_work_doubles(int n, int m) {
 LB_HD size_t lb_work_ints(int n) { return 2 * (size_t)n; }
 
 LB_FN void lb_carve(LbWork &w, double *dbase, int *ibase, int n, int m) {
+  // t r d z | W | sy ss yy tinv are contiguous and in the order of the persisted per-start
+  // block, so that staging a start in and out is three linear copies
   double *q = dbase;
-  w.x = q; q += n; w.g = q; q += n; w.z = q; q += n; w.r = q; q += n;
-  w.d = q; q += n; w.t = q; q += n; w.xp = q; q += n;
+  w.x = q; q += n; w.g = q; q += n; w.xp = q; q += n;
+  w.t = q; q += n; w.r = q; q += n; w.d = q; q += n; w.z = q; q += n;
   w.W = q; q += (size_t)n * LB_LDW(m);
   w.sy = q; q += m * m; w.ss = q; q += m * m; w.yy = q; q += m * m; w.tinv = q; q += m * m;
   w.ld = q; q += m * m;
@@ -137,13 +167,16 @@ LB_FN void lb_carve(LbWork &w, double *dbase, int *ibase, int n, int m) {
   w.p = q; q += 2 * m; w.c = q; q += 2 * m; w.wbp = q; q += 2 * m; w.v = q; q += 2 * m;
   w.q = q; q += 2 * m;
   w.iwhere = ibase; w.index = ibase + n;
+  w.ftab = nullptr;
 }
 
 // ------------------------------------------------------------------ small dense kernels
 // Cholesky A = R'R in place, R in the upper triangle (LINPACK dpofa); rd[k] = 1/R[k][k].
 // 0 ok, else k+1.  Right-looking: after column k is scaled, lane j owns column k+1+j of the
 // trailing block and walks its rows, so there is no index arithmetic in the inner loop.
-LB_FN int lb_chol(double *A, int ld, int n, double *rd) {
+LB_NI int lb_chol(double *A, int ld, int n, double *rd) {
+  LB_SHARED(A); LB_SHARED(rd);
+  LB_UNROLL1
   for (int k = 0; k < n; ++k) {
     LB_SYNC();
     const double akk = A[k * ld + k];
@@ -154,11 +187,14 @@ LB_FN int lb_chol(double *A, int ld, int n, double *rd) {
 #else
     const double rinv = 1.0 / rkk;
 #endif
+    LB_UNROLL1
     for (int j = k + 1 + LB_LANE; j < n; j += LB_NL) A[k * ld + j] *= rinv;
     LB_SYNC();
     if (LB_LANE == 0) { A[k * ld + k] = rkk; rd[k] = rinv; }
+    LB_UNROLL1
     for (int j = k + 1 + LB_LANE; j < n; j += LB_NL) {
       const double akj = A[k * ld + j];
+      LB_UNROLL1
       for (int i = k + 1; i <= j; ++i) A[i * ld + j] -= A[k * ld + i] * akj;
     }
   }
@@ -169,11 +205,13 @@ LB_FN int lb_chol(double *A, int ld, int n, double *rd) {
 // solve R' x = b (R upper; dtrsl job 11), b overwritten; n <= 32 on the device, where lane i
 // keeps b[i] in a register and the pivot travels by shuffle (no shared-memory round trip in
 // the serial chain).  rd = reciprocal diagonal from lb_chol.
-LB_FN void lb_trsl_t(const double *R, int ld, int n, const double *rd, double *b) {
+LB_NI void lb_trsl_t(const double *R, int ld, int n, const double *rd, double *b) {
+  LB_SHARED(R); LB_SHARED(rd); LB_SHARED(b);
   LB_SYNC();
 #if LB_WARP
   const int i = LB_LANE;
   double bi = i < n ? b[i] : 0.0;
+  LB_UNROLL1
   for (int k = 0; k < n; ++k) {
     const double rki = (i > k && i < n) ? R[k * ld + i] : 0.0;
     const double xk = __shfl_sync(0xffffffffu, bi, k) * rd[k];
@@ -182,9 +220,11 @@ LB_FN void lb_trsl_t(const double *R, int ld, int n, const double *rd, double *b
   }
   if (i < n) b[i] = bi;
 #else
+  LB_UNROLL1
   for (int k = 0; k < n; ++k) {
     const double xk = b[k] * rd[k];
     b[k] = xk;
+    LB_UNROLL1
     for (int i = k + 1; i < n; ++i) b[i] -= R[k * ld + i] * xk;
   }
 #endif
@@ -192,11 +232,13 @@ LB_FN void lb_trsl_t(const double *R, int ld, int n, const double *rd, double *b
 }
 
 // solve R x = b (R upper; dtrsl job 01), b overwritten
-LB_FN void lb_trsl_n(const double *R, int ld, int n, const double *rd, double *b) {
+LB_NI void lb_trsl_n(const double *R, int ld, int n, const double *rd, double *b) {
+  LB_SHARED(R); LB_SHARED(rd); LB_SHARED(b);
   LB_SYNC();
 #if LB_WARP
   const int i = LB_LANE;
   double bi = i < n ? b[i] : 0.0;
+  LB_UNROLL1
   for (int k = n - 1; k >= 0; --k) {
     const double rik = i < k ? R[i * ld + k] : 0.0;
     const double xk = __shfl_sync(0xffffffffu, bi, k) * rd[k];
@@ -205,9 +247,11 @@ LB_FN void lb_trsl_n(const double *R, int ld, int n, const double *rd, double *b
   }
   if (i < n) b[i] = bi;
 #else
+  LB_UNROLL1
   for (int k = n - 1; k >= 0; --k) {
     const double xk = b[k] * rd[k];
     b[k] = xk;
+    LB_UNROLL1
     for (int i = 0; i < k; ++i) b[i] -= R[i * ld + k] * xk;
   }
 #endif
@@ -219,31 +263,38 @@ LB_FN void lb_prep_ld(LbWork &w, int m, int col) {
   LB_SYNC();
   LB_FOR(k, col) w.ld[k * m + k] = 1.0 / w.sy[k * m + k];
   LB_SYNC();
+  LB_UNROLL1
   for (int i = 1; i < col; ++i)
+    LB_UNROLL1
     for (int k = LB_LANE; k < i; k += LB_NL) w.ld[i * m + k] = w.sy[i * m + k] * w.ld[k * m + k];
   LB_SYNC();
 }
 
 // p = M v with M the inverse 2col x 2col middle matrix of the compact L-BFGS formula (bmv),
 // through the precomputed operators tinv and ld (see LbWork).  v and p must not alias.
-LB_FN void lb_bmv(const LbWork &w, int m, int col, const double *v, double *p) {
+LB_NI void lb_bmv(const double *ld, const double *tinv, double *q, int m, int col,
+                  const double *v, double *p) {
+  LB_SHARED(ld); LB_SHARED(tinv); LB_SHARED(q); LB_SHARED(v); LB_SHARED(p);
   if (col == 0) return;
   LB_SYNC();
   LB_FOR(i, col) {
     double a = v[col + i];
-    for (int k = 0; k < i; ++k) a += w.ld[i * m + k] * v[k];
-    w.q[i] = a;
+    LB_UNROLL1
+    for (int k = 0; k < i; ++k) a += ld[i * m + k] * v[k];
+    q[i] = a;
   }
   LB_SYNC();
   LB_FOR(i, col) {
     double a = 0.0;
-    for (int j = 0; j < col; ++j) a += w.tinv[i * m + j] * w.q[j];
+    LB_UNROLL1
+    for (int j = 0; j < col; ++j) a += tinv[i * m + j] * q[j];
     p[col + i] = a;
   }
   LB_SYNC();
   LB_FOR(i, col) {
-    double a = -w.ld[i * m + i] * v[i];
-    for (int k = i + 1; k < col; ++k) a += w.ld[k * m + i] * p[col + k];
+    double a = -ld[i * m + i] * v[i];
+    LB_UNROLL1
+    for (int k = i + 1; k < col; ++k) a += ld[k * m + i] * p[col + k];
     p[i] = a;
   }
   LB_SYNC();
@@ -256,26 +307,34 @@ LB_FN int lb_formt(LbWork &w, int m, int col, double theta) {
   double *T = w.wn;             // [col][m] upper triangle -> R
   double *Ri = w.wn + m * m;    // [col][m] upper triangle: R^-1
   lb_prep_ld(w, m, col);
+  LB_UNROLL1
   for (int i = 0; i < col; ++i)
+    LB_UNROLL1
     for (int j = i + LB_LANE; j < col; j += LB_NL) {
       double a = theta * w.ss[i * m + j];
+      LB_UNROLL1
       for (int k = 0; k < i; ++k) a += w.ld[i * m + k] * w.sy[j * m + k];
       T[i * m + j] = a;
     }
   if (lb_chol(T, m, col, w.rd)) return -3;
   // R^-1 column by column (lane j solves R x = e_j by back substitution; rows > j are zero)
   LB_FOR(j, col) {
+    LB_UNROLL1
     for (int k = j; k >= 0; --k) {
       double a = k == j ? 1.0 : 0.0;
+      LB_UNROLL1
       for (int i = k + 1; i <= j; ++i) a -= T[k * m + i] * Ri[i * m + j];
       Ri[k * m + j] = a * w.rd[k];
     }
   }
   LB_SYNC();
   // T^-1 = R^-1 R^-T (symmetric, stored full)
+  LB_UNROLL1
   for (int i = 0; i < col; ++i)
+    LB_UNROLL1
     for (int j = i + LB_LANE; j < col; j += LB_NL) {
       double a = 0.0;
+      LB_UNROLL1
       for (int k = j; k < col; ++k) a += Ri[i * m + k] * Ri[j * m + k];
       w.tinv[i * m + j] = a;
       w.tinv[j * m + i] = a;
@@ -285,16 +344,18 @@ LB_FN int lb_formt(LbWork &w, int m, int col, double theta) {
 }
 
 // ------------------------------------------------------------------ projected gradient norm
-LB_FN double lb_projgr(const LbParams &P, const LbDP x, const LbDP g) {
+LB_NI double lb_projgr(int n, const int *nbd, const double *lo, const double *hi, const double *x,
+                       const double *g) {
+  LB_SHARED(x); LB_SHARED(g);
   double s = 0.0;
-  LB_FOR(i, P.n) {
+  LB_FOR(i, n) {
     double gi = g[i];
-    const int nb = P.nbd[i];
+    const int nb = nbd[i];
     if (nb != 0) {
       if (gi < 0.0) {
-        if (nb >= 2) gi = fmax(x[i] - P.hi[i], gi);
+        if (nb >= 2) gi = fmax(x[i] - hi[i], gi);
       } else {
-        if (nb <= 2) gi = fmin(x[i] - P.lo[i], gi);
+        if (nb <= 2) gi = fmin(x[i] - lo[i], gi);
       }
     }
     s = fmax(s, fabs(gi));
@@ -354,9 +415,11 @@ LB_FN int lb_cauchy(const LbParams &P, LbWork &w, const LbScal &s, int &nseg_out
   const bool bnded = !lb_any(unb);
   LB_SYNC();
   // p = W'd (ws half scaled by theta), c = 0
+  LB_UNROLL1
   for (int j = LB_LANE; j < col2; j += LB_NL) {
     const LbDP wc = w.W + (j < col ? j : m + (j - col));
     double a = 0.0;
+    LB_UNROLL1
     for (int i = 0; i < n; ++i) a += wc[i * ldw] * d[i];
     w.p[j] = j < col ? a : theta * a;
     w.c[j] = 0.0;
@@ -367,8 +430,9 @@ LB_FN int lb_cauchy(const LbParams &P, LbWork &w, const LbScal &s, int &nseg_out
   double f2 = -theta * f1;
   const double f2_org = f2;
   if (col > 0) {
-    lb_bmv(w, m, col, w.p, w.v);
+    lb_bmv(w.ld, w.tinv, w.q, m, col, w.p, w.v);
     double a = 0.0;
+    LB_UNROLL1
     for (int j = LB_LANE; j < col2; j += LB_NL) a += w.v[j] * w.p[j];
     f2 -= lb_sum(a);
   }
@@ -378,15 +442,16 @@ LB_FN int lb_cauchy(const LbParams &P, LbWork &w, const LbScal &s, int &nseg_out
   if (nbreak > 0) {
     int nleft = nbreak;
     double tj = 0.0;
+    LB_UNROLL1
     for (;;) {
       const double tj0 = tj;
       // smallest remaining breakpoint
       double bv = LB_INF;
       int bi = 0x7fffffff;
       LB_FOR(i, n) if (tb[i] < bv) { bv = tb[i]; bi = i; }
-      lb_argmin(bv, bi);
-      tj = bv;
-      const int ibp = bi;
+      const LbArgMin am = lb_argmin(bv, bi);
+      tj = am.v;
+      const int ibp = am.idx;
       const double dt = tj - tj0;
       if (dtm < dt) break;  // minimiser inside this segment
       tsum += dt;
@@ -413,12 +478,14 @@ LB_FN int lb_cauchy(const LbParams &P, LbWork &w, const LbScal &s, int &nseg_out
       f1 = f1 + dt * f2 + dibp2 - theta * dibp * zibp;
       f2 = f2 - theta * dibp2;
       if (col > 0) {
+        LB_UNROLL1
         for (int j = LB_LANE; j < col2; j += LB_NL) {
           w.c[j] += dt * w.p[j];
           w.wbp[j] = j < col ? w.W[ibp * ldw + j] : theta * w.W[ibp * ldw + m + (j - col)];
         }
-        lb_bmv(w, m, col, w.wbp, w.v);
+        lb_bmv(w.ld, w.tinv, w.q, m, col, w.wbp, w.v);
         double wmc = 0.0, wmp = 0.0, wmw = 0.0;
+        LB_UNROLL1
         for (int j = LB_LANE; j < col2; j += LB_NL) {
           const double vj = w.v[j];
           wmc += w.c[j] * vj;
@@ -444,6 +511,7 @@ LB_FN int lb_cauchy(const LbParams &P, LbWork &w, const LbScal &s, int &nseg_out
     LB_FOR(i, n) xcp[i] += tsum * d[i];
   }
   if (col > 0)
+    LB_UNROLL1
     for (int j = LB_LANE; j < col2; j += LB_NL) w.c[j] += dtm * w.p[j];
   LB_SYNC();
   nseg_out = nseg;
@@ -464,6 +532,7 @@ LB_FN int lb_freev(const LbParams &P, LbWork &w) {
     LB_FOR(i, n) c += (w.iwhere[i] <= 0);
     nfree_total = lb_isum(c);
   }
+  LB_UNROLL1
   for (int i0 = 0; i0 < n; i0 += 32) {
     const int i = i0 + LB_LANE;
     const bool valid = i < n;
@@ -481,6 +550,7 @@ LB_FN int lb_freev(const LbParams &P, LbWork &w) {
 #else
   // serial variants sweep all n variables with the iwhere mask instead of an index list
   int nfree = 0;
+  LB_UNROLL1
   for (int i = 0; i < n; ++i) nfree += (w.iwhere[i] <= 0);
   return nfree;
 #endif
@@ -497,26 +567,32 @@ LB_FN int lb_freev(const LbParams &P, LbWork &w) {
 // YY, SS, SY kept up to date by matupd.  Output o of the 2*tri+col^2 sums is owned by lane
 // o % 32, which keeps it in a register while the warp walks the rows of Q.
 #define LB_FORMK_ACC 7  // ceil((2*55 + 100) / 32) for m = 10
-LB_FN void lb_formk_decode(int o, int col, int m, int &type, int &i, int &j, int &ca, int &cb) {
-  const int ntri = col * (col + 1) / 2;
+// The map output -> (family, i, j, column pair) is enumerated over the FULL m x m shapes
+// (2*55 + 100 = 210 outputs for m = 10) so that it does not depend on col: it is tabulated
+// once per CTA (lb_formk_table, LB_FORMK_ACC*32 ints in shared memory) and the entries with
+// i >= col or j >= col are simply not written out.
+//   code = ty | i << 2 | j << 8 | ca << 14 | cb << 22
+LB_FN int lb_formk_code(int o, int m) {
+  const int ntri = m * (m + 1) / 2;
+  int ty, i, j, ca, cb;
+  if (o >= 2 * ntri + m * m) return 0;
   if (o < 2 * ntri) {
-    type = o >= ntri;
-    int q = type ? o - ntri : o;
-    // q = i*(i+1)/2 + j, i >= j: closed-form unranking, corrected for rounding
-    i = (int)((sqrtf(8.f * (float)q + 1.f) - 1.f) * 0.5f);
-    if ((i + 1) * (i + 2) / 2 <= q) ++i;
-    if (i * (i + 1) / 2 > q) --i;
+    ty = o >= ntri;
+    const int q = ty ? o - ntri : o;
+    i = 0;
+    while ((i + 1) * (i + 2) / 2 <= q) ++i;  // q = i*(i+1)/2 + j, i >= j
     j = q - i * (i + 1) / 2;
-    ca = type ? m + i : i;
-    cb = type ? m + j : j;
+    ca = ty ? m + i : i;
+    cb = ty ? m + j : j;
   } else {
-    type = 2;
+    ty = 2;
     const int q = o - 2 * ntri;
-    i = q / col;  // s index
-    j = q - i * col;  // y index
+    i = q / m;      // s index
+    j = q - i * m;  // y index
     ca = m + i;
     cb = j;
   }
+  return ty | i << 2 | j << 8 | ca << 14 | cb << 22;
 }
 
 #if !LB_WARP
@@ -530,6 +606,7 @@ LB_FN void lb_gram_sym(const LbParams &P, const LbWork &w, int col, int coff, do
   double acc[LB_MMAX * (LB_MMAX + 1) / 2];
 #pragma unroll
   for (int e = 0; e < LB_MMAX * (LB_MMAX + 1) / 2; ++e) acc[e] = 0.0;
+  LB_UNROLL1
   for (int i = 0; i < n; ++i) {
     if (w.iwhere[i] > 0) continue;
     const LbDP row = w.W + (i * ldw + coff);
@@ -551,6 +628,7 @@ LB_FN void lb_gram_sy(const LbParams &P, const LbWork &w, int col, double *out) 
   double acc[NA * LB_MMAX];
 #pragma unroll
   for (int e = 0; e < NA * LB_MMAX; ++e) acc[e] = 0.0;
+  LB_UNROLL1
   for (int i = 0; i < n; ++i) {
     if (w.iwhere[i] > 0) continue;
     const LbDP row = w.W + i * ldw;
@@ -578,30 +656,34 @@ LB_FN int lb_formk(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
   const bool over_free = nfree <= n - nfree;
   const LbIP ind = over_free ? w.index : w.index + nfree;
   const int nq = over_free ? nfree : n - nfree;
-  const int ntri = col * (col + 1) / 2;
-  const int nout = 2 * ntri + col * col;
+  const int nout = m * (m + 1) + m * m;
   double acc[LB_FORMK_ACC];
-  int code[LB_FORMK_ACC];  // ty | i << 2 | j << 8 | ca << 14 | cb << 22
+  int code[LB_FORMK_ACC];
 #pragma unroll
   for (int t = 0; t < LB_FORMK_ACC; ++t) {
-    int ty = 0, i = 0, j = 0, ca = 0, cb = 0;
-    const int o = LB_LANE + 32 * t;
     acc[t] = 0.0;
-    if (o < nout) lb_formk_decode(o, col, m, ty, i, j, ca, cb);
-    code[t] = ty | i << 2 | j << 8 | ca << 14 | cb << 22;
+    code[t] = w.ftab[LB_LANE + 32 * t];
   }
+  LB_UNROLL1
   for (int k = 0; k < nq; ++k) {
     const LbDP row = W + ind[k] * ldw;
 #pragma unroll
     for (int t = 0; t < LB_FORMK_ACC; ++t)
       acc[t] += row[(code[t] >> 14) & 255] * row[(code[t] >> 22) & 255];
   }
+  // write-out as a ROLLED loop (one copy of the code instead of seven): the accumulators take
+  // a detour through a dynamically indexed (local-memory) array
+  double accm[LB_FORMK_ACC];
 #pragma unroll
+  for (int t = 0; t < LB_FORMK_ACC; ++t) accm[t] = acc[t];
+  LB_UNROLL1
   for (int t = 0; t < LB_FORMK_ACC; ++t) {
     const int o = LB_LANE + 32 * t;
-    if (o >= nout) continue;
-    const int ty = code[t] & 3, i = (code[t] >> 2) & 63, j = (code[t] >> 8) & 63;
-    const double g = acc[t];
+    if (o >= nout) break;
+    const int cd = w.ftab[o];
+    const int ty = cd & 3, i = (cd >> 2) & 63, j = (cd >> 8) & 63;
+    if (i >= col || j >= col) continue;
+    const double g = accm[t];
     if (ty == 0) {         // Y'ZZ'Y/theta + D at (j, i), i >= j
       double a = over_free ? g : w.yy[i * m + j] - g;
       a /= theta;
@@ -620,19 +702,25 @@ LB_FN int lb_formk(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
   {
     double G[LB_MMAX * LB_MMAX];  // one family at a time
     lb_gram_sym(P, w, col, 0, G);  // Y'ZZ'Y
+    LB_UNROLL1
     for (int i = 0; i < col; ++i)
+      LB_UNROLL1
       for (int j = 0; j <= i; ++j) {
         double a = G[i * (i + 1) / 2 + j] / theta;
         if (i == j) a += w.sy[i * m + i];
         w.wn[j * ldn + i] = a;
       }
     lb_gram_sym(P, w, col, m, G);  // S'ZZ'S; the active part is the total minus it
+    LB_UNROLL1
     for (int i = 0; i < col; ++i)
+      LB_UNROLL1
       for (int j = 0; j <= i; ++j)
         w.wn[(col + j) * ldn + (col + i)] = (w.ss[i * m + j] - G[i * (i + 1) / 2 + j]) * theta;
     lb_gram_sy<0>(P, w, col, G);   // S'ZZ'Y, s index i, y index j
     lb_gram_sy<LB_MMAX / 2>(P, w, col, G);
+    LB_UNROLL1
     for (int i = 0; i < col; ++i)
+      LB_UNROLL1
       for (int j = 0; j < col; ++j) {
         const double g = G[i * LB_MMAX + j];
         w.wn[j * ldn + (col + i)] = j >= i ? g : -(w.sy[i * m + j] - g);
@@ -646,17 +734,22 @@ LB_FN int lb_formk(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
   {
     const int js = col + LB_LANE % col, isub = LB_LANE / col;
     const int nsub = LB_NL >= col ? LB_NL / col : 1;
+    LB_UNROLL1
     for (int k = 0; k < col; ++k) {
+      LB_UNROLL1
       for (int c = col + LB_LANE; c < 2 * col; c += LB_NL) w.wn[k * ldn + c] *= w.rd[k];
       LB_SYNC();
 #if LB_WARP
       if (isub < nsub) {
         const double xk = w.wn[k * ldn + js];
+        LB_UNROLL1
         for (int i = k + 1 + isub; i < col; i += nsub) w.wn[i * ldn + js] -= w.wn[k * ldn + i] * xk;
       }
 #else
+      LB_UNROLL1
       for (int c = col; c < 2 * col; ++c) {
         const double xk = w.wn[k * ldn + c];
+        LB_UNROLL1
         for (int i = k + 1; i < col; ++i) w.wn[i * ldn + c] -= w.wn[k * ldn + i] * xk;
       }
       (void)js; (void)isub; (void)nsub;
@@ -665,9 +758,12 @@ LB_FN int lb_formk(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
     }
   }
   // (2,2) block += (1,2)'(1,2), upper triangle
+  LB_UNROLL1
   for (int is = col; is < 2 * col; ++is)
+    LB_UNROLL1
     for (int js = is + LB_LANE; js < 2 * col; js += LB_NL) {
       double a = 0.0;
+      LB_UNROLL1
       for (int k = 0; k < col; ++k) a += w.wn[k * ldn + is] * w.wn[k * ldn + js];
       w.wn[is * ldn + js] += a;
     }
@@ -686,11 +782,12 @@ LB_FN int lb_cmprlb(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
     LB_SYNC();
     return 0;
   }
-  lb_bmv(w, m, col, w.c, w.p);
+  lb_bmv(w.ld, w.tinv, w.q, m, col, w.c, w.p);
   LB_FOR(i, n) {
     if (w.iwhere[i] <= 0) {
       double a = -theta * (w.z[i] - w.x[i]) - w.g[i];
       const LbDP row = w.W + i * ldw;
+      LB_UNROLL1
       for (int j = 0; j < col; ++j) a += row[j] * w.p[j] + row[m + j] * (theta * w.p[col + j]);
       w.r[i] = a;
     } else {
@@ -712,9 +809,11 @@ LB_FN int lb_subsm(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
   LB_SYNC();
   // wv = W'Z d
 #if LB_WARP
+  LB_UNROLL1
   for (int j = LB_LANE; j < col2; j += LB_NL) {
     const LbDP wc = w.W + (j < col ? j : m + (j - col));
     double a = 0.0;
+    LB_UNROLL1
     for (int k = 0; k < nfree; ++k) { const int i = w.index[k]; a += wc[i * ldw] * w.r[i]; }
     wv[j] = j < col ? a : theta * a;
   }
@@ -723,6 +822,7 @@ LB_FN int lb_subsm(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
     double acc[2 * LB_MMAX];
 #pragma unroll
     for (int a = 0; a < 2 * LB_MMAX; ++a) acc[a] = 0.0;
+    LB_UNROLL1
     for (int i = 0; i < n; ++i) {
       if (w.iwhere[i] > 0) continue;
       const double ri = w.r[i];
@@ -738,8 +838,10 @@ LB_FN int lb_subsm(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
 #endif
   // wv := K^-1 wv  (the first col entries are pre-divided by theta for the loop below)
   lb_trsl_t(w.wn, ldn, col2, w.rd, wv);
+  LB_UNROLL1
   for (int j = LB_LANE; j < col; j += LB_NL) wv[j] = -wv[j];
   lb_trsl_n(w.wn, ldn, col2, w.rd, wv);
+  LB_UNROLL1
   for (int j = LB_LANE; j < col; j += LB_NL) wv[j] /= theta;
   LB_SYNC();
   // d = (1/theta) d + (1/theta^2) Z'W wv ; xp = xcp ; projected Newton point
@@ -750,6 +852,7 @@ LB_FN int lb_subsm(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
     if (w.iwhere[i] <= 0) {
       double dk = w.r[i];
       const LbDP row = w.W + i * ldw;
+      LB_UNROLL1
       for (int j = 0; j < col; ++j) dk += row[j] * wv[j] + row[m + j] * wv[col + j];
       dk *= 1.0 / theta;
       w.r[i] = dk;
@@ -801,7 +904,10 @@ LB_FN int lb_subsm(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
         if (ratio < amin) { amin = ratio; ibd = i; }
       }
     }
-    lb_argmin(amin, ibd);
+    {
+      const LbArgMin am = lb_argmin(amin, ibd);
+      amin = am.v; ibd = am.idx;
+    }
     double alpha = 1.0;
     LB_SYNC();
     if (amin < 1.0) {
@@ -832,6 +938,7 @@ LB_FN void lb_matupd(const LbParams &P, LbWork &w, LbScal &s, double rr, double 
   } else {
     LB_FOR(i, n) {
       LbDP row = w.W + i * ldw;
+      LB_UNROLL1
       for (int j = 0; j < m - 1; ++j) { row[j] = row[j + 1]; row[m + j] = row[m + j + 1]; }
     }
     // new(i,j) = old(i+1,j+1) for the three (m-1) x (m-1) leading blocks: lane j owns column j
@@ -839,8 +946,10 @@ LB_FN void lb_matupd(const LbParams &P, LbWork &w, LbScal &s, double rr, double 
     // comes from the column to its right (owned by lane j+1) -- hence read all, sync, write all
     const int c1 = s.col - 1;
     LbDP mats[3] = {w.sy, w.ss, w.yy};
+    LB_UNROLL1
     for (int q = 0; q < 3; ++q) {
       LbDP A = mats[q];
+      LB_UNROLL1
       for (int i = 0; i < c1; ++i) {
         double tmp = 0.0;
         const int j = LB_LANE;
@@ -849,6 +958,7 @@ LB_FN void lb_matupd(const LbParams &P, LbWork &w, LbScal &s, double rr, double 
         LB_SYNC();
         if (j < c1) A[i * m + j] = tmp;
 #else
+        LB_UNROLL1
         for (int jj = 0; jj < c1; ++jj) A[i * m + jj] = A[(i + 1) * m + jj + 1];
         (void)tmp; (void)j;
 #endif
@@ -864,11 +974,13 @@ LB_FN void lb_matupd(const LbParams &P, LbWork &w, LbScal &s, double rr, double 
   LB_SYNC();
   // products of the new pair with every older column j: lane j < last pairs y_j with (s,y),
   // lane last + j pairs s_j with (s,y)
+  LB_UNROLL1
   for (int jl = LB_LANE; jl < 2 * last; jl += LB_NL) {
     const bool is_y = jl < last;
     const int j = is_y ? jl : jl - last;
     const LbDP colp = w.W + (is_y ? j : m + j);
     double a_s = 0.0, a_y = 0.0;
+    LB_UNROLL1
     for (int i = 0; i < n; ++i) {
       const double c = colp[i * ldw];
       a_s += w.d[i] * c;
@@ -917,7 +1029,7 @@ LB_FN int lb_advance(const LbParams &P, LbWork &w, LbScal &s, Mem &mem, int stag
   if (stage == 2) {
     st = s.resume;
   } else if (s.phase == LB_PH_START) {
-    s.sbgnrm = lb_projgr(P, w.x, w.g);
+    s.sbgnrm = lb_projgr(n, P.nbd, P.lo, P.hi, w.x, w.g);
     if (s.sbgnrm <= P.pgtol) { lb_finish(s, 0, 401); return 0; }
     st = ST_ITER;
   } else {
@@ -929,7 +1041,7 @@ LB_FN int lb_advance(const LbParams &P, LbWork &w, LbScal &s, Mem &mem, int stag
     if (s.ls_task == LB_LS_CONV || s.ls_task == LB_LS_WARN) {
       // NEW_X
       s.iter += 1;
-      s.sbgnrm = lb_projgr(P, w.x, w.g);
+      s.sbgnrm = lb_projgr(n, P.nbd, P.lo, P.hi, w.x, w.g);
       // driver (scipy/optimize/_lbfgsb_py.py:421-434)
       s.nit += 1;
       if (s.nit >= P.maxiter) { lb_finish(s, 1, 504); return 0; }
@@ -942,6 +1054,7 @@ LB_FN int lb_advance(const LbParams &P, LbWork &w, LbScal &s, Mem &mem, int stag
     }
   }
 
+  LB_UNROLL1
   for (;;) {
     if (st == ST_TESTS) {
       // ---- termination tests (mainlb label 777) ----
@@ -982,6 +1095,7 @@ LB_FN int lb_advance(const LbParams &P, LbWork &w, LbScal &s, Mem &mem, int stag
       // ---- new iteration (label 222): search direction ----
       mem.dirty_vec();
       int nfree = n;
+      LB_UNROLL1
       for (;;) {
         if (!P.cnstnd && s.col > 0) {
           LB_SYNC();
@@ -1050,7 +1164,7 @@ LB_FN int lb_advance(const LbParams &P, LbWork &w, LbScal &s, Mem &mem, int stag
       if (s.gd >= 0.0) {
         st = ST_FAIL;  // not a descent direction (info = -4)
       } else {
-        lb_dcsrch(s, s.f, s.gd);
+        lb_dcsrch_start(s, s.f, s.gd);
         st = s.ls_task == LB_LS_ERROR ? ST_FAIL : ST_REQUEST;
       }
     }

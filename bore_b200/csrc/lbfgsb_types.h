@@ -147,24 +147,28 @@ LB_HD void lb_dcstep(double &stx, double &fx, double &dx, double &sty, double &f
 
 // ------------------------------------------------------------------ line search (dcsrch)
 // ftol 1e-3, gtol 0.9, xtol 0.1, stpmin 0 -- the constants lnsrlb passes.
+// first call of a search (task START): set up the interval, ask for f,g at the first step
+LB_HD void lb_dcsrch_start(LbScal &s, double f, double g) {
+  const double ftol = 1e-3, stpmin = 0.0, xtrapu = 4.0;
+  const double stpmax = s.stpmx;
+  if (s.stp < stpmin || s.stp > stpmax || g >= 0.0) { s.ls_task = LB_LS_ERROR; return; }
+  s.brackt = 0;
+  s.stage = 1;
+  s.finit = f; s.ginit = g; s.gtest = ftol * g;
+  s.width = stpmax - stpmin;
+  s.width1 = s.width / 0.5;
+  s.stx = 0.0; s.fx = f; s.gx = g;
+  s.sty = 0.0; s.fy = f; s.gy = g;
+  s.stmin = 0.0;
+  s.stmax = s.stp + xtrapu * s.stp;
+  s.ls_task = LB_LS_FG;
+}
+// every later call (task FG): f,g at the trial step have arrived
 LB_HD void lb_dcsrch(LbScal &s, double f, double g) {
   const double ftol = 1e-3, gtol = 0.9, xtol = 0.1, stpmin = 0.0;
   const double stpmax = s.stpmx;
   const double xtrapl = 1.1, xtrapu = 4.0;
-  if (s.ls_task == LB_LS_START) {
-    if (s.stp < stpmin || s.stp > stpmax || g >= 0.0) { s.ls_task = LB_LS_ERROR; return; }
-    s.brackt = 0;
-    s.stage = 1;
-    s.finit = f; s.ginit = g; s.gtest = ftol * g;
-    s.width = stpmax - stpmin;
-    s.width1 = s.width / 0.5;
-    s.stx = 0.0; s.fx = f; s.gx = g;
-    s.sty = 0.0; s.fy = f; s.gy = g;
-    s.stmin = 0.0;
-    s.stmax = s.stp + xtrapu * s.stp;
-    s.ls_task = LB_LS_FG;
-    return;
-  }
+  (void)ftol;
   const double ftest = s.finit + s.stp * s.gtest;
   if (s.stage == 1 && f <= ftest && g >= 0.0) s.stage = 2;
   int task = LB_LS_FG;
@@ -174,18 +178,25 @@ LB_HD void lb_dcsrch(LbScal &s, double f, double g) {
   if (s.stp == stpmin && (f > ftest || g >= s.gtest)) task = LB_LS_WARN;
   if (f <= ftest && fabs(g) <= gtol * (-s.ginit)) task = LB_LS_CONV;
   if (task != LB_LS_FG) { s.ls_task = task; return; }
-  if (s.stage == 1 && f <= s.fx && f > ftest) {
-    const double fm = f - s.stp * s.gtest;
-    double fxm = s.fx - s.stx * s.gtest, fym = s.fy - s.sty * s.gtest;
-    const double gm = g - s.gtest;
-    double gxm = s.gx - s.gtest, gym = s.gy - s.gtest;
-    lb_dcstep(s.stx, fxm, gxm, s.sty, fym, gym, s.stp, fm, gm, s.brackt, s.stmin, s.stmax);
-    s.fx = fxm + s.stx * s.gtest;
-    s.fy = fym + s.sty * s.gtest;
-    s.gx = gxm + s.gtest;
-    s.gy = gym + s.gtest;
-  } else {
-    lb_dcstep(s.stx, s.fx, s.gx, s.sty, s.fy, s.gy, s.stp, f, g, s.brackt, s.stmin, s.stmax);
+  {
+    // one dcstep call site for both branches (the modified-function branch works on shifted
+    // copies and shifts back afterwards; the arithmetic is the original's)
+    const bool mod = s.stage == 1 && f <= s.fx && f > ftest;
+    double fxv = s.fx, fyv = s.fy, gxv = s.gx, gyv = s.gy, fv = f, gv = g;
+    if (mod) {
+      fv = f - s.stp * s.gtest;
+      fxv = s.fx - s.stx * s.gtest; fyv = s.fy - s.sty * s.gtest;
+      gv = g - s.gtest;
+      gxv = s.gx - s.gtest; gyv = s.gy - s.gtest;
+    }
+    lb_dcstep(s.stx, fxv, gxv, s.sty, fyv, gyv, s.stp, fv, gv, s.brackt, s.stmin, s.stmax);
+    if (mod) {
+      fxv = fxv + s.stx * s.gtest;
+      fyv = fyv + s.sty * s.gtest;
+      gxv = gxv + s.gtest;
+      gyv = gyv + s.gtest;
+    }
+    s.fx = fxv; s.fy = fyv; s.gx = gxv; s.gy = gyv;
   }
   if (s.brackt) {
     if (fabs(s.sty - s.stx) >= 0.66 * s.width1) s.stp = s.stx + 0.5 * (s.sty - s.stx);
