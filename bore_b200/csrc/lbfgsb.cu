@@ -45,7 +45,7 @@ namespace lbw {  // warp-collective variant
 }  // namespace lbw
 namespace {
 
-constexpr int SCAL_BYTES = 256;
+constexpr int SCAL_BYTES = LB_SCAL_DOUBLES * sizeof(double);
 static_assert(sizeof(LbScal) <= SCAL_BYTES, "LbScal grew past its slot");
 
 struct LbLayout {
@@ -69,8 +69,7 @@ inline LbLayout make_layout(int S, int n, int m) {
   L.g = o; o += align_up((size_t)S * n * sizeof(float), 16);
   L.pend = o; o += align_up((size_t)S * sizeof(int), 16);
   o = align_up(o, 256);
-  L.block_stride = align_up(SCAL_BYTES + ((size_t)4 * n + (size_t)n * LB_LDW(m) +
-                                          LB_NPERSIST_MM * m * m) * sizeof(double), 128);
+  L.block_stride = align_up((size_t)LB_PERSIST_DOUBLES(n, m) * sizeof(double), 128);
   L.blocks = o; o += L.block_stride * S;
   L.total = o;
   return L;
@@ -94,12 +93,6 @@ struct LbDev {
 
 __device__ __forceinline__ LbScal *scal_of(const LbDev &D, int sid) {
   return reinterpret_cast<LbScal *>(D.blocks + D.block_stride * sid);
-}
-
-__device__ __forceinline__ int init_iwhere(const LbParams &P, int i) {
-  const int nb = P.nbd[i];
-  if (nb == 0) return -1;
-  return (nb == 2 && P.hi[i] - P.lo[i] <= 0.0) ? 3 : 0;
 }
 
 // algorithmic bytes of one step: what an ideal implementation has to move --
@@ -158,56 +151,81 @@ __global__ void __launch_bounds__(128) lbfgsb_init_kernel(LbDev D, const double 
 }
 
 // ---------------------------------------------------------------- warp variant: one round
-// linear staging copies between a start's persisted block (HBM) and the warp's workspace;
-// real functions so that the kernel holds one copy of each (code size, see lbfgsb_core.h)
-__device__ __noinline__ void lb_g2s(double *dst, const double *__restrict__ src, int cnt) {
-  __builtin_assume(__isShared(dst));
-#pragma unroll 1
-  for (int i = threadIdx.x & 31; i < cnt; i += 32) dst[i] = src[i];
+// TMA bulk copies (cp.async.bulk, SASS UBLKCP) stage a start's persisted block between HBM and
+// the warp's workspace: one instruction per direction instead of a load/store loop whose
+// iterations each wait out an HBM round trip.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
 }
-__device__ __noinline__ void lb_s2g(double *__restrict__ dst, const double *src, int cnt) {
-  __builtin_assume(__isShared(src));
-#pragma unroll 1
-  for (int i = threadIdx.x & 31; i < cnt; i += 32) dst[i] = src[i];
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LB_DONE;\n"
+      "bra LB_WAIT;\n"
+      "LB_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+               "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() {  // source smem of all committed stores is free
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() {  // all committed stores have landed
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() {  // generic-proxy smem writes -> async proxy
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// lazy loader of the limited-memory matrices (state block -> the warp's smem workspace);
-// W | sy ss yy tinv are contiguous in both places
+// the limited-memory matrices arrive with the rest of the block; `load` only derives L D^-1
 struct BlockMem {
   const LbParams &P;
   lbw::LbWork &w;
   LbScal &s;
-  double *gW;  // this start's W, followed by [sy ss yy tinv], in HBM
   bool loaded = false, is_dirty = false, vec_dirty = false;
-  __device__ BlockMem(const LbParams &P_, lbw::LbWork &w_, LbScal &s_, double *gW_)
-      : P(P_), w(w_), s(s_), gW(gW_) {}
-  __device__ int count() const { return P.n * LB_LDW(P.m) + LB_NPERSIST_MM * P.m * P.m; }
+  __device__ BlockMem(const LbParams &P_, lbw::LbWork &w_, LbScal &s_) : P(P_), w(w_), s(s_) {}
   __device__ void load() {
     if (loaded) return;
     loaded = true;
-    if (s.col == 0) return;  // empty memory: nothing valid to read
-    lb_g2s(w.W, gW, count());
-    __syncwarp();
+    if (s.col == 0) return;  // empty memory: nothing valid
     lbw::lb_prep_ld(w, P.m, s.col);
   }
   __device__ void dirty() { is_dirty = true; }
   __device__ void dirty_vec() { vec_dirty = true; }
-  __device__ void store() {
-    if (!is_dirty) return;
-    __syncwarp();
-    lb_s2g(gW, w.W, count());
-  }
 };
 
-// CTA header in dynamic shared memory: the formk output map, then lo / hi / nbd
-__host__ __device__ inline size_t lb_header_bytes(int n) {
+// CTA header in dynamic shared memory: formk output map | lo | hi | nbd | one mbarrier per warp
+__host__ __device__ inline size_t lb_header_bytes(int n, int wpb) {
   return align_up(LB_FORMK_ACC * 32 * sizeof(int), 16) + 2 * align_up(n * sizeof(double), 16) +
-         align_up(n * sizeof(int), 16);
+         align_up(n * sizeof(int), 16) + align_up(wpb * sizeof(uint64_t), 16);
 }
 
 template <typename FG>
 __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t warp_bytes) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int n = D.P.n, m = D.P.m;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -218,11 +236,28 @@ __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t w
   const int *list_cur = D.lists + (size_t)(round & 1) * D.S;
   int *list_nxt = D.lists + (size_t)((round + 1) & 1) * D.S;
 
-  // ---- CTA header: formk map, bounds ----
+  // ---- CTA header ----
   int *ftab = reinterpret_cast<int *>(smem_raw);
   double *s_lo = reinterpret_cast<double *>(smem_raw + align_up(LB_FORMK_ACC * 32 * sizeof(int), 16));
   double *s_hi = s_lo + align_up(n * sizeof(double), 16) / sizeof(double);
   int *s_nbd = reinterpret_cast<int *>(s_hi + align_up(n * sizeof(double), 16) / sizeof(double));
+  uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(s_nbd) +
+                                                align_up(n * sizeof(int), 16));
+  uint64_t *bar = bars + wib;
+  unsigned char *base = smem_raw + lb_header_bytes(n, wpb) + warp_bytes * wib;
+  const uint32_t block_bytes = (uint32_t)(LB_PERSIST_DOUBLES(n, m) * sizeof(double));
+  const int stride = gridDim.x * wpb;
+  int idx = blockIdx.x * wpb + wib;
+
+  // the first start's block is on its way while the header is being filled
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (idx < n_active) {
+      mbar_expect_tx(bar, block_bytes);
+      bulk_g2s(base, D.blocks + D.block_stride * list_cur[idx], block_bytes, bar);
+    }
+  }
 #pragma unroll 1
   for (int o = threadIdx.x; o < LB_FORMK_ACC * 32; o += blockDim.x) ftab[o] = lbw::lb_formk_code(o, m);
 #pragma unroll 1
@@ -235,23 +270,26 @@ __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t w
   LbParams P = D.P;
   P.lo = s_lo; P.hi = s_hi; P.nbd = s_nbd;
 
-  unsigned char *base = smem_raw + lb_header_bytes(n) + warp_bytes * wib;
   lbw::LbWork w;
   lbw::lb_carve(w, reinterpret_cast<double *>(base),
                 reinterpret_cast<int *>(base + lbw::lb_work_doubles(n, m) * sizeof(double)), n, m);
   w.ftab = ftab;
+  LbScal *s_smem = reinterpret_cast<LbScal *>(base);
   const FG *F = static_cast<const FG *>(D.F);
   const FG *G = static_cast<const FG *>(D.G);
+  uint32_t parity = 0;
 
 #pragma unroll 1
-  for (int idx = blockIdx.x * wpb + wib; idx < n_active; idx += gridDim.x * wpb) {
+  for (; idx < n_active; idx += stride) {
     const int sid = list_cur[idx];
-    LbScal s = *scal_of(D, sid);
-    double *gvec = reinterpret_cast<double *>(D.blocks + D.block_stride * sid + SCAL_BYTES);
+    char *gblock = D.blocks + D.block_stride * sid;
     double *xr = D.xreq + (size_t)sid * n;
     const FG *gr = G + (size_t)sid * n;
+    // pull the block of this warp's next start into L2 while this one is being worked on
+    if (lane == 0 && idx + stride < n_active)
+      bulk_prefetch_l2(D.blocks + D.block_stride * list_cur[idx + stride], block_bytes);
 
-    s.f = (double)F[sid];
+    const double fval = (double)F[sid];
 #pragma unroll 1
     for (int i = lane; i < n; i += 32) {
       w.x[i] = xr[i];
@@ -259,9 +297,12 @@ __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t w
       const int nb = s_nbd[i];
       w.iwhere[i] = nb == 0 ? -1 : ((nb == 2 && s_hi[i] - s_lo[i] <= 0.0) ? 3 : 0);
     }
-    if (s.phase == LB_PH_LNSRCH) lb_g2s(w.t, gvec, 4 * n);  // t r d z
+    mbar_wait(bar, parity);
+    parity ^= 1;
     __syncwarp();
-    BlockMem mem(P, w, s, gvec + 4 * n);
+    LbScal s = *s_smem;
+    s.f = fval;
+    BlockMem mem(P, w, s);
     const int col_in = s.col;
     const bool was_ls = s.phase == LB_PH_LNSRCH;
     const int pend = lbw::lb_advance(P, w, s, mem);
@@ -280,22 +321,36 @@ __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t w
         if (xf) xf[i] = (float)xi;
       }
       if (__any_sync(0xffffffffu, changed)) s.nfev += 1;
-      if (mem.vec_dirty) lb_s2g(gvec, w.t, 4 * n);
-      mem.store();
-      if (lane == 0) {
+    } else {
+#pragma unroll 1
+      for (int i = lane; i < n; i += 32) xr[i] = w.x[i];  // final iterate
+    }
+    // write back the head of the block that changed: scalars | t r d z | W and the matrices
+    if (lane == 0) *s_smem = s;
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      uint32_t bytes = SCAL_BYTES;
+      if (pend && mem.vec_dirty) bytes += 4 * LB_NV(n) * sizeof(double);
+      if (pend && mem.is_dirty) bytes = block_bytes;
+      bulk_s2g(gblock, base, bytes);
+      bulk_commit();
+      if (pend) {
         const int pos = atomicAdd(&D.cnt[nxt], 1);
         list_nxt[pos] = sid;
         atomicAdd(D.evals, 1ULL);
       }
-    } else {
-      lb_s2g(xr, w.x, n);  // final iterate
-    }
-    if (lane == 0) {
-      *scal_of(D, sid) = s;
       if (D.pend) D.pend[sid] = pend;
+      // the workspace may be overwritten once the store has read it
+      bulk_wait_read();
+      if (idx + stride < n_active) {
+        mbar_expect_tx(bar, block_bytes);
+        bulk_g2s(base, D.blocks + D.block_stride * list_cur[idx + stride], block_bytes, bar);
+      }
     }
     __syncwarp();
   }
+  if (lane == 0) bulk_wait_all();
 }
 
 __global__ void lbfgsb_results_kernel(LbDev D, double *x, double *fun, int *nit, int *nfev,
@@ -338,7 +393,7 @@ struct StepLaunch {
 
 int plan_step(int S, int n, int m, int sm_count, StepLaunch &L) {
   L.warp_bytes = align_up(lbw::lb_work_doubles(n, m) * sizeof(double) + lbw::lb_work_ints(n) * sizeof(int), 16);
-  const size_t hdr = lb_header_bytes(n);
+  const size_t hdr = lb_header_bytes(n, 12);
   const size_t max_block = 227 * 1024, max_sm = 228 * 1024;  // per CTA (opt-in) / per SM
   BORE_CHECK(L.warp_bytes + hdr <= max_block, "lbfgsb: n=%d needs %zu B of shared memory per start", n,
              L.warp_bytes + hdr);

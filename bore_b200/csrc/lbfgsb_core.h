@@ -149,18 +149,18 @@ struct LbWork {
 };
 
 LB_HD size_t lb_work_doubles(int n, int m) {
-  return (size_t)7 * n + (size_t)n * LB_LDW(m) + 5 * m * m + 4 * m * m + 12 * m;
+  return (size_t)LB_PERSIST_DOUBLES(n, m) + 3 * LB_NV(n) + 5 * m * m + 12 * m;
 }
 LB_HD size_t lb_work_ints(int n) { return 2 * (size_t)n; }
 
 LB_FN void lb_carve(LbWork &w, double *dbase, int *ibase, int n, int m) {
-  // t r d z | W | sy ss yy tinv are contiguous and in the order of the persisted per-start
-  // block, so that staging a start in and out is three linear copies
-  double *q = dbase;
-  w.x = q; q += n; w.g = q; q += n; w.xp = q; q += n;
-  w.t = q; q += n; w.r = q; q += n; w.d = q; q += n; w.z = q; q += n;
-  w.W = q; q += (size_t)n * LB_LDW(m);
+  // persisted block first (see LB_PERSIST_DOUBLES), scratch after it
+  const int nv = LB_NV(n);
+  double *q = dbase + LB_SCAL_DOUBLES;
+  w.t = q; q += nv; w.r = q; q += nv; w.d = q; q += nv; w.z = q; q += nv;
+  w.W = q; q += LB_NW(n, m);
   w.sy = q; q += m * m; w.ss = q; q += m * m; w.yy = q; q += m * m; w.tinv = q; q += m * m;
+  w.x = q; q += nv; w.g = q; q += nv; w.xp = q; q += nv;
   w.ld = q; q += m * m;
   w.wn = q; q += 4 * m * m;
   w.rd = q; q += 2 * m;

@@ -64,6 +64,15 @@ struct LbScal {
 #define LB_LDW(m) (2 * (m) + 1)
 // persisted small matrices per start: sy ss yy tinv, each [m][m]
 #define LB_NPERSIST_MM 4
+// A start's persisted block, in this order in HBM *and* at the head of its workspace, so that
+// staging it in or out is ONE linear (bulk) copy:
+//   scalars (LbScal, LB_SCAL_DOUBLES doubles) | t r d z (4 x LB_NV) | W (LB_NW) | sy ss yy tinv
+// Vector and W extents are rounded up to even counts: every piece starts 16-byte aligned.
+#define LB_SCAL_DOUBLES 32
+#define LB_NV(n) (((n) + 1) & ~1)
+#define LB_NW(n, m) (((n) * LB_LDW(m) + 1) & ~1)
+#define LB_PERSIST_DOUBLES(n, m) \
+  (LB_SCAL_DOUBLES + 4 * LB_NV(n) + LB_NW(n, m) + LB_NPERSIST_MM * (m) * (m))
 
 // ------------------------------------------------------------------ More'-Thuente step (dcstep)
 LB_HD void lb_dcstep(double &stx, double &fx, double &dx, double &sty, double &fy, double &dy,
