@@ -200,19 +200,11 @@ __device__ __forceinline__ void fence_async_smem() {  // generic-proxy smem writ
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// the limited-memory matrices arrive with the rest of the block; `load` only derives L D^-1
+// the limited-memory matrices arrive with the rest of the block; only the bookkeeping of what
+// has to be written back is left
 struct BlockMem {
-  const LbParams &P;
-  lbw::LbWork &w;
-  LbScal &s;
   bool loaded = false, is_dirty = false, vec_dirty = false;
-  __device__ BlockMem(const LbParams &P_, lbw::LbWork &w_, LbScal &s_) : P(P_), w(w_), s(s_) {}
-  __device__ void load() {
-    if (loaded) return;
-    loaded = true;
-    if (s.col == 0) return;  // empty memory: nothing valid
-    lbw::lb_prep_ld(w, P.m, s.col);
-  }
+  __device__ void load() { loaded = true; }
   __device__ void dirty() { is_dirty = true; }
   __device__ void dirty_vec() { vec_dirty = true; }
 };
@@ -302,7 +294,7 @@ __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t w
     __syncwarp();
     LbScal s = *s_smem;
     s.f = fval;
-    BlockMem mem(P, w, s);
+    BlockMem mem;
     const int col_in = s.col;
     const bool was_ls = s.phase == LB_PH_LNSRCH;
     const int pend = lbw::lb_advance(P, w, s, mem);

@@ -149,7 +149,7 @@ struct LbWork {
 };
 
 LB_HD size_t lb_work_doubles(int n, int m) {
-  return (size_t)LB_PERSIST_DOUBLES(n, m) + 3 * LB_NV(n) + 5 * m * m + 12 * m;
+  return (size_t)LB_PERSIST_DOUBLES(n, m) + 3 * LB_NV(n) + 4 * m * m + 12 * m;
 }
 LB_HD size_t lb_work_ints(int n) { return 2 * (size_t)n; }
 
@@ -160,8 +160,8 @@ LB_FN void lb_carve(LbWork &w, double *dbase, int *ibase, int n, int m) {
   w.t = q; q += nv; w.r = q; q += nv; w.d = q; q += nv; w.z = q; q += nv;
   w.W = q; q += LB_NW(n, m);
   w.sy = q; q += m * m; w.ss = q; q += m * m; w.yy = q; q += m * m; w.tinv = q; q += m * m;
-  w.x = q; q += nv; w.g = q; q += nv; w.xp = q; q += nv;
   w.ld = q; q += m * m;
+  w.x = q; q += nv; w.g = q; q += nv; w.xp = q; q += nv;
   w.wn = q; q += 4 * m * m;
   w.rd = q; q += 2 * m;
   w.p = q; q += 2 * m; w.c = q; q += 2 * m; w.wbp = q; q += 2 * m; w.v = q; q += 2 * m;
@@ -174,32 +174,65 @@ LB_FN void lb_carve(LbWork &w, double *dbase, int *ibase, int n, int m) {
 // Cholesky A = R'R in place, R in the upper triangle (LINPACK dpofa); rd[k] = 1/R[k][k].
 // 0 ok, else k+1.  Right-looking: after column k is scaled, lane j owns column k+1+j of the
 // trailing block and walks its rows, so there is no index arithmetic in the inner loop.
+#if LB_WARP
+// sqrt(a) and 1/sqrt(a); one copy of the two (long) fp64 sequences for the unrolled callers
+struct LbRoots { double root, rinv; };
+LB_NI LbRoots lb_roots(double a) {
+  LbRoots r;
+  r.root = sqrt(a);
+  r.rinv = rsqrt(a);
+  return r;
+}
+#endif
 LB_NI int lb_chol(double *A, int ld, int n, double *rd) {
   LB_SHARED(A); LB_SHARED(rd);
-  LB_UNROLL1
+#if LB_WARP
+  // n <= LB_MMAX.  Lane j keeps column j of the upper triangle in registers; the scaled pivot
+  // row travels by shuffle, so the only shared-memory traffic is one load and one store of
+  // the matrix.  The matrix is padded with the identity up to LB_MMAX, which makes every
+  // loop bound a compile-time constant (no branches around the shuffles); below the diagonal
+  // the registers fill with the mirror image, which nothing reads.  Same operations in the
+  // same order as the serial form below.
+  LB_SYNC();
+  const int j = LB_LANE;
+  double a[LB_MMAX];
+#pragma unroll
+  for (int i = 0; i < LB_MMAX; ++i) {
+    a[i] = i == j ? 1.0 : 0.0;
+    if (j < n && i <= j) a[i] = A[i * ld + j];
+  }
+#pragma unroll
+  for (int k = 0; k < LB_MMAX; ++k) {
+    const double akk = __shfl_sync(0xffffffffu, a[k], k);
+    if (!(akk > 0.0)) return k + 1;
+    const LbRoots rt = lb_roots(akk);
+    const double akj = a[k] * rt.rinv;
+    a[k] = j == k ? rt.root : akj;
+    if (j == k && k < n) rd[k] = rt.rinv;
+#pragma unroll
+    for (int i = k + 1; i < LB_MMAX; ++i) a[i] -= __shfl_sync(0xffffffffu, akj, i) * akj;  // lane i holds R[k][i]
+  }
+#pragma unroll
+  for (int i = 0; i < LB_MMAX; ++i)
+    if (j < n && i <= j) A[i * ld + j] = a[i];
+  LB_SYNC();
+  return 0;
+#else
   for (int k = 0; k < n; ++k) {
-    LB_SYNC();
     const double akk = A[k * ld + k];
     if (!(akk > 0.0)) return k + 1;
     const double rkk = sqrt(akk);
-#if LB_WARP
-    const double rinv = rsqrt(akk);  // independent of the sqrt: both issue back to back
-#else
     const double rinv = 1.0 / rkk;
-#endif
-    LB_UNROLL1
-    for (int j = k + 1 + LB_LANE; j < n; j += LB_NL) A[k * ld + j] *= rinv;
-    LB_SYNC();
-    if (LB_LANE == 0) { A[k * ld + k] = rkk; rd[k] = rinv; }
-    LB_UNROLL1
-    for (int j = k + 1 + LB_LANE; j < n; j += LB_NL) {
+    for (int j = k + 1; j < n; ++j) A[k * ld + j] *= rinv;
+    A[k * ld + k] = rkk;
+    rd[k] = rinv;
+    for (int j = k + 1; j < n; ++j) {
       const double akj = A[k * ld + j];
-      LB_UNROLL1
       for (int i = k + 1; i <= j; ++i) A[i * ld + j] -= A[k * ld + i] * akj;
     }
   }
-  LB_SYNC();
   return 0;
+#endif
 }
 
 // solve R' x = b (R upper; dtrsl job 11), b overwritten; n <= 32 on the device, where lane i
@@ -258,15 +291,27 @@ LB_NI void lb_trsl_n(const double *R, int ld, int n, const double *rd, double *b
   LB_SYNC();
 }
 
+// Flat work sharing for the m x m triangles: pair p < m(m+1)/2 -> (i, j) with i >= j comes from
+// the CTA's table (the family-0 entries of lb_formk_code), so that all 32 lanes share the 55
+// pairs of a triangle instead of <= 10 lanes walking its columns.
+#define LB_PAIR_HI(cd) (((cd) >> 2) & 63)
+#define LB_PAIR_LO(cd) (((cd) >> 8) & 63)
+
 // ld = L D^-1 below the diagonal, 1/D on it (L, D = strictly lower part / diagonal of SY)
 LB_FN void lb_prep_ld(LbWork &w, int m, int col) {
   LB_SYNC();
   LB_FOR(k, col) w.ld[k * m + k] = 1.0 / w.sy[k * m + k];
   LB_SYNC();
-  LB_UNROLL1
+#if LB_WARP
+  LB_FOR(p, m * (m + 1) / 2) {
+    const int cd = w.ftab[p];
+    const int i = LB_PAIR_HI(cd), k = LB_PAIR_LO(cd);
+    if (i < col && k < i) w.ld[i * m + k] = w.sy[i * m + k] * w.ld[k * m + k];
+  }
+#else
   for (int i = 1; i < col; ++i)
-    LB_UNROLL1
-    for (int k = LB_LANE; k < i; k += LB_NL) w.ld[i * m + k] = w.sy[i * m + k] * w.ld[k * m + k];
+    for (int k = 0; k < i; ++k) w.ld[i * m + k] = w.sy[i * m + k] * w.ld[k * m + k];
+#endif
   LB_SYNC();
 }
 
@@ -307,40 +352,78 @@ LB_FN int lb_formt(LbWork &w, int m, int col, double theta) {
   double *T = w.wn;             // [col][m] upper triangle -> R
   double *Ri = w.wn + m * m;    // [col][m] upper triangle: R^-1
   lb_prep_ld(w, m, col);
-  LB_UNROLL1
-  for (int i = 0; i < col; ++i)
-    LB_UNROLL1
-    for (int j = i + LB_LANE; j < col; j += LB_NL) {
+#if LB_WARP
+  const int npair = m * (m + 1) / 2;
+  LB_FOR(p, npair) {
+    const int cd = w.ftab[p];
+    const int j = LB_PAIR_HI(cd), i = LB_PAIR_LO(cd);  // i <= j
+    if (j < col) {
       double a = theta * w.ss[i * m + j];
       LB_UNROLL1
       for (int k = 0; k < i; ++k) a += w.ld[i * m + k] * w.sy[j * m + k];
       T[i * m + j] = a;
     }
+  }
   if (lb_chol(T, m, col, w.rd)) return -3;
-  // R^-1 column by column (lane j solves R x = e_j by back substitution; rows > j are zero)
-  LB_FOR(j, col) {
-    LB_UNROLL1
-    for (int k = j; k >= 0; --k) {
+  // R^-1: lane j solves R x = e_j by back substitution with its column in registers; the
+  // entries of R are the same for every lane (broadcast loads)
+  {
+    const int j = LB_LANE;
+    double x[LB_MMAX];
+#pragma unroll
+    for (int k = LB_MMAX - 1; k >= 0; --k) {
       double a = k == j ? 1.0 : 0.0;
-      LB_UNROLL1
-      for (int i = k + 1; i <= j; ++i) a -= T[k * m + i] * Ri[i * m + j];
-      Ri[k * m + j] = a * w.rd[k];
+#pragma unroll
+      for (int i = k + 1; i < LB_MMAX; ++i) {
+        const double t = (i < col) ? T[k * m + i] : 0.0;
+        a -= t * x[i];  // x[i] == 0 for i > j
+      }
+      x[k] = (k <= j && k < col) ? a * w.rd[k] : 0.0;
     }
+#pragma unroll
+    for (int k = 0; k < LB_MMAX; ++k)
+      if (j < col && k <= j) Ri[k * m + j] = x[k];
   }
   LB_SYNC();
   // T^-1 = R^-1 R^-T (symmetric, stored full)
-  LB_UNROLL1
-  for (int i = 0; i < col; ++i)
-    LB_UNROLL1
-    for (int j = i + LB_LANE; j < col; j += LB_NL) {
+  LB_FOR(p, npair) {
+    const int cd = w.ftab[p];
+    const int j = LB_PAIR_HI(cd), i = LB_PAIR_LO(cd);  // i <= j
+    if (j < col) {
       double a = 0.0;
       LB_UNROLL1
       for (int k = j; k < col; ++k) a += Ri[i * m + k] * Ri[j * m + k];
       w.tinv[i * m + j] = a;
       w.tinv[j * m + i] = a;
     }
+  }
   LB_SYNC();
   return 0;
+#else
+  for (int i = 0; i < col; ++i)
+    for (int j = i; j < col; ++j) {
+      double a = theta * w.ss[i * m + j];
+      for (int k = 0; k < i; ++k) a += w.ld[i * m + k] * w.sy[j * m + k];
+      T[i * m + j] = a;
+    }
+  if (lb_chol(T, m, col, w.rd)) return -3;
+  // R^-1 column by column (back substitution of R x = e_j; rows > j are zero)
+  for (int j = 0; j < col; ++j)
+    for (int k = j; k >= 0; --k) {
+      double a = k == j ? 1.0 : 0.0;
+      for (int i = k + 1; i <= j; ++i) a -= T[k * m + i] * Ri[i * m + j];
+      Ri[k * m + j] = a * w.rd[k];
+    }
+  // T^-1 = R^-1 R^-T (symmetric, stored full)
+  for (int i = 0; i < col; ++i)
+    for (int j = i; j < col; ++j) {
+      double a = 0.0;
+      for (int k = j; k < col; ++k) a += Ri[i * m + k] * Ri[j * m + k];
+      w.tinv[i * m + j] = a;
+      w.tinv[j * m + i] = a;
+    }
+  return 0;
+#endif
 }
 
 // ------------------------------------------------------------------ projected gradient norm
@@ -729,44 +812,56 @@ LB_FN int lb_formk(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
 #endif
   // Cholesky of the (1,1) block
   if (lb_chol(w.wn, ldn, col, w.rd)) return -1;
-  // (1,2) block := L11^-1 (1,2): right-looking forward elimination over all col right-hand
-  // sides at once (lane -> (row offset, rhs) fixed outside the loop)
-  {
-    const int js = col + LB_LANE % col, isub = LB_LANE / col;
-    const int nsub = LB_NL >= col ? LB_NL / col : 1;
-    LB_UNROLL1
-    for (int k = 0; k < col; ++k) {
-      LB_UNROLL1
-      for (int c = col + LB_LANE; c < 2 * col; c += LB_NL) w.wn[k * ldn + c] *= w.rd[k];
-      LB_SYNC();
 #if LB_WARP
-      if (isub < nsub) {
-        const double xk = w.wn[k * ldn + js];
-        LB_UNROLL1
-        for (int i = k + 1 + isub; i < col; i += nsub) w.wn[i * ldn + js] -= w.wn[k * ldn + i] * xk;
+  // (1,2) block := R11^-T (1,2): lane c carries right-hand side c through the forward
+  // substitution in registers; the entries of R11 are broadcast loads
+  {
+    const int c = LB_LANE;
+    double b[LB_MMAX];
+#pragma unroll
+    for (int k = 0; k < LB_MMAX; ++k) b[k] = (k < col && c < col) ? w.wn[k * ldn + col + c] : 0.0;
+#pragma unroll
+    for (int i = 0; i < LB_MMAX; ++i) {
+#pragma unroll
+      for (int k = 0; k < i; ++k) {
+        const double t = (i < col) ? w.wn[k * ldn + i] : 0.0;
+        b[i] -= t * b[k];
       }
-#else
+      b[i] *= (i < col) ? w.rd[i] : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < LB_MMAX; ++k)
+      if (k < col && c < col) w.wn[k * ldn + col + c] = b[k];
+  }
+  LB_SYNC();
+  // (2,2) block += (1,2)'(1,2), upper triangle, the 55 pairs shared by all lanes
+  LB_FOR(p, m * (m + 1) / 2) {
+    const int cd = w.ftab[p];
+    const int js = LB_PAIR_HI(cd), is = LB_PAIR_LO(cd);  // is <= js
+    if (js < col) {
+      double a = 0.0;
       LB_UNROLL1
-      for (int c = col; c < 2 * col; ++c) {
-        const double xk = w.wn[k * ldn + c];
-        LB_UNROLL1
-        for (int i = k + 1; i < col; ++i) w.wn[i * ldn + c] -= w.wn[k * ldn + i] * xk;
-      }
-      (void)js; (void)isub; (void)nsub;
-#endif
-      LB_SYNC();
+      for (int k = 0; k < col; ++k) a += w.wn[k * ldn + col + is] * w.wn[k * ldn + col + js];
+      w.wn[(col + is) * ldn + col + js] += a;
+    }
+  }
+#else
+  // (1,2) block := R11^-T (1,2): forward elimination over all col right-hand sides
+  for (int k = 0; k < col; ++k) {
+    for (int c = col; c < 2 * col; ++c) w.wn[k * ldn + c] *= w.rd[k];
+    for (int c = col; c < 2 * col; ++c) {
+      const double xk = w.wn[k * ldn + c];
+      for (int i = k + 1; i < col; ++i) w.wn[i * ldn + c] -= w.wn[k * ldn + i] * xk;
     }
   }
   // (2,2) block += (1,2)'(1,2), upper triangle
-  LB_UNROLL1
   for (int is = col; is < 2 * col; ++is)
-    LB_UNROLL1
-    for (int js = is + LB_LANE; js < 2 * col; js += LB_NL) {
+    for (int js = is; js < 2 * col; ++js) {
       double a = 0.0;
-      LB_UNROLL1
       for (int k = 0; k < col; ++k) a += w.wn[k * ldn + is] * w.wn[k * ldn + js];
       w.wn[is * ldn + js] += a;
     }
+#endif
   if (lb_chol(w.wn + col * ldn + col, ldn, col, w.rd + col)) return -2;
   return 0;
 }
@@ -941,29 +1036,30 @@ LB_FN void lb_matupd(const LbParams &P, LbWork &w, LbScal &s, double rr, double 
       LB_UNROLL1
       for (int j = 0; j < m - 1; ++j) { row[j] = row[j + 1]; row[m + j] = row[m + j + 1]; }
     }
-    // new(i,j) = old(i+1,j+1) for the three (m-1) x (m-1) leading blocks: lane j owns column j
-    // and walks down it, so every read of a column happens before the write that replaces it
-    // comes from the column to its right (owned by lane j+1) -- hence read all, sync, write all
+    // new(i,j) = old(i+1,j+1) for the three (m-1) x (m-1) leading blocks of sy, ss, yy
+    // (contiguous, m*m apart): lane q*c1 + j owns column j of matrix q and walks down it; a row
+    // is read in the iteration before the one that overwrites it, hence one sync per row
     const int c1 = s.col - 1;
-    LbDP mats[3] = {w.sy, w.ss, w.yy};
-    LB_UNROLL1
-    for (int q = 0; q < 3; ++q) {
-      LbDP A = mats[q];
+#if LB_WARP
+    if (c1 > 0) {
+      const int q = LB_LANE / c1, j = LB_LANE - q * c1;
+      LbDP A = w.sy + q * m * m;
       LB_UNROLL1
       for (int i = 0; i < c1; ++i) {
         double tmp = 0.0;
-        const int j = LB_LANE;
-#if LB_WARP
-        if (j < c1) tmp = A[(i + 1) * m + j + 1];
+        if (q < 3) tmp = A[(i + 1) * m + j + 1];
         LB_SYNC();
-        if (j < c1) A[i * m + j] = tmp;
-#else
-        LB_UNROLL1
-        for (int jj = 0; jj < c1; ++jj) A[i * m + jj] = A[(i + 1) * m + jj + 1];
-        (void)tmp; (void)j;
-#endif
+        if (q < 3) A[i * m + j] = tmp;
       }
     }
+#else
+    LbDP mats[3] = {w.sy, w.ss, w.yy};
+    for (int q = 0; q < 3; ++q) {
+      LbDP A = mats[q];
+      for (int i = 0; i < c1; ++i)
+        for (int jj = 0; jj < c1; ++jj) A[i * m + jj] = A[(i + 1) * m + jj + 1];
+    }
+#endif
   }
   const int col = s.col, last = col - 1;
   LB_FOR(i, n) {

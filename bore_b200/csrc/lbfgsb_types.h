@@ -62,11 +62,12 @@ struct LbScal {
 };
 
 #define LB_LDW(m) (2 * (m) + 1)
-// persisted small matrices per start: sy ss yy tinv, each [m][m]
-#define LB_NPERSIST_MM 4
+// persisted small matrices per start: sy ss yy tinv ld, each [m][m] (ld = L D^-1 is derived
+// from sy, but keeping it costs 6 % more block bytes and saves recomputing it every step)
+#define LB_NPERSIST_MM 5
 // A start's persisted block, in this order in HBM *and* at the head of its workspace, so that
 // staging it in or out is ONE linear (bulk) copy:
-//   scalars (LbScal, LB_SCAL_DOUBLES doubles) | t r d z (4 x LB_NV) | W (LB_NW) | sy ss yy tinv
+//   scalars (LbScal, LB_SCAL_DOUBLES doubles) | t r d z (4 x LB_NV) | W (LB_NW) | sy ss yy tinv ld
 // Vector and W extents are rounded up to even counts: every piece starts 16-byte aligned.
 #define LB_SCAL_DOUBLES 32
 #define LB_NV(n) (((n) + 1) & ~1)

@@ -33,7 +33,7 @@ funcs, src = [], []
 if hdr_path:
     src = open(hdr_path).read().split("\n")
     for i, l in enumerate(src, 1):
-        m = re.match(r"(?:LB_HD|__device__|template).*?\b(\w+)\(", l)
+        m = re.match(r"(?:LB_HD|LB_FN|LB_NI|__device__|template).*?\b(\w+)\(", l)
         if m and not l.startswith(" "): funcs.append((i, m.group(1)))
 def fn(c):
     if c is None: return "none"
