@@ -50,6 +50,8 @@ int bore_mlp_create(int n_layers, const int *dims, const int *acts, int n_models
   BORE_CUDA(cudaSetDevice(device));
   bore_mlp *h = new bore_mlp();
   memset(h, 0, sizeof(*h));
+  h->pack = new MlpPackCache();
+  memset(h->pack, 0, sizeof(*h->pack));
   MlpDesc &d = h->desc;
   d.n_layers = n_layers;
   int off = 0;
@@ -86,6 +88,10 @@ int bore_mlp_destroy(bore_mlp *h) {
   cudaFree(h->adam_m);
   cudaFree(h->adam_v);
   cudaFree(h->adam_t);
+  if (h->pack) {
+    for (int v = 0; v < 4; ++v) cudaFree(h->pack->buf[v]);
+    delete h->pack;
+  }
   delete h;
   return 0;
 }

@@ -40,8 +40,17 @@ struct MlpDesc {
   int n_params;
 };
 
+// K0/K2 stage their weights from a pre-packed, zero-padded image (one per kernel variant:
+// grad / no grad x narrow / wide lane mapping) with a single bulk copy; the cache is shared by
+// shallow copies of the handle.
+struct MlpPackCache {
+  float *buf[4];
+  size_t cap[4];  // floats allocated
+};
+
 struct bore_mlp {
   MlpDesc desc;
+  MlpPackCache *pack;
   int n_models;
   int device;
   int sm_count;
@@ -59,11 +68,14 @@ static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 // K0 / K2.  `list` (may be NULL) is a device array of row indices: point i of the launch
 // is row list[i] of X / f / g (used by the L-BFGS-B driver's compacted active list);
 // `n_dev` (may be NULL) is a device int holding the number of points (<= S).
+// `prepacked` != 0: the caller has run mlp_eval_prepare for these models since the parameters
+// last changed (the L-BFGS-B driver packs once per call, not once per round).
 int launch_mlp_eval(const bore_mlp *h, int model, bool want_grad, int transform, int negate,
                     const float *X, int S, float *f, float *g, const int *list,
-                    const int *n_dev, cudaStream_t stream);
+                    const int *n_dev, cudaStream_t stream, int prepacked = 0);
+int mlp_eval_prepare(const bore_mlp *h, int model0, int n_models, bool want_grad, cudaStream_t stream);
 // batched problems (BASELINE.json configs[3]): one CTA per model; model model0+b owns points
 // [b*per_model, (b+1)*per_model) of X / f / g; `flags` (may be NULL) selects the points to do.
 int launch_mlp_eval_multi(const bore_mlp *h, int model0, int n_models, int per_model, bool want_grad,
                           int transform, int negate, const float *X, float *f, float *g,
-                          const int *flags, cudaStream_t stream);
+                          const int *flags, cudaStream_t stream, int prepacked = 0);

@@ -525,6 +525,8 @@ static int minimize_impl(bore_mlp *h, int model, int n_models, int per_model, in
     lbfgsb_init_kernel<<<blocks, 128, 0, stream>>>(D, X0_dev);
     BORE_CUDA(cudaGetLastError());
   }
+  // the weight image K2 stages from: packed once per call, not once per round
+  if (mlp_eval_prepare(h, model, n_models, true, stream)) return -1;
   // pipelined polling: the active counter of chunk c is read while chunk c+1 is in flight
   const int CHUNK = 4;
   int *cnt_host = nullptr;
@@ -542,9 +544,9 @@ static int minimize_impl(bore_mlp *h, int model, int n_models, int per_model, in
       if (g_prof.enabled) cudaEventRecord(g_prof.get(3 * (size_t)round), stream);
       rc = per_model > 0
                ? launch_mlp_eval_multi(h, model, n_models, per_model, true, transform, 1, D.xf, F, G,
-                                       D.pend, stream)
+                                       D.pend, stream, 1)
                : launch_mlp_eval(h, model, true, transform, 1, D.xf, S, F, G, list, D.cnt + round % 3,
-                                 stream);
+                                 stream, 1);
       if (rc) break;
       if (g_prof.enabled) cudaEventRecord(g_prof.get(3 * (size_t)round + 1), stream);
       rc = launch_round<float>(D, SL, round, stream);

@@ -111,14 +111,55 @@ __device__ __forceinline__ void tile_gemm(const float *__restrict__ A, const flo
   }
 }
 
+// Writes one model's zero-padded weight image (the shared-memory plan of mlp_eval_kernel) to
+// global memory: grid = models, launched once per parameter change instead of re-deriving the
+// image in every CTA of every launch.
+__global__ void __launch_bounds__(256)
+mlp_pack_kernel(const MlpDesc d, const SmemPlan P, int CH, int grad, const float *__restrict__ params_all,
+                float *__restrict__ packed_all) {
+  const float *params = params_all + (size_t)blockIdx.x * d.n_params;
+  float *out = packed_all + (size_t)blockIdx.x * P.weights_total;
+  const int G = d.n_layers - 1;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  for (int l = 0; l < G; ++l) {
+    const int in = d.dims[l], outd = d.dims[l + 1];
+    const int in4 = rup(in, 4), outP = rup(outd, CH);
+    const float *Wg = params + d.w_off[l];
+    float *wf = out + P.wf[l];
+    for (int e = tid; e < in4 * outP; e += nthr) {
+      const int k = e / outP, j = e - k * outP;
+      wf[e] = (k < in && j < outd) ? Wg[k * outd + j] : 0.f;
+    }
+    float *bs = out + P.bias[l];
+    for (int e = tid; e < outP; e += nthr) bs[e] = e < outd ? params[d.b_off[l] + e] : 0.f;
+    if (grad) {
+      const int out4 = rup(outd, 4), inP = rup(in, CH);
+      float *wb = out + P.wb[l];
+      for (int e = tid; e < out4 * inP; e += nthr) {
+        const int j = e / inP, k = e - j * inP;
+        wb[e] = (k < in && j < outd) ? Wg[k * outd + j] : 0.f;
+      }
+    }
+  }
+  {
+    const int in = d.dims[G];
+    float *wl = out + P.wl;
+    for (int e = tid; e < P.weights_total - P.wl; e += nthr)
+      wl[e] = e < in ? params[d.w_off[G] + e] : 0.f;  // incl. the pad up to weights_total
+  }
+}
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 template <bool GRAD, int UGB>
 __global__ void __launch_bounds__(512)
 mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ params,
-                const float *__restrict__ X,
+                const float *__restrict__ packed, const float *__restrict__ X,
                 int S, const int *__restrict__ n_dev, const int *__restrict__ list,
                 float *__restrict__ f_out, float *__restrict__ g_out, int transform, float sign,
                 int per_model, const int *__restrict__ flags) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t s_bar;
   using M = Map<UGB>;
   constexpr int TP = M::TP, AST = M::AST, CH = M::CH, UG = M::UG;
   const int G = d.n_layers - 1;
@@ -133,6 +174,7 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
   int *llist = reinterpret_cast<int *>(smem + P.weights_total + (nthr >> 5) * P.warp_total);
   if (multi) {
     params += (size_t)blockIdx.x * d.n_params;
+    packed += (size_t)blockIdx.x * P.weights_total;
     row_base = (long)blockIdx.x * per_model;
     if (flags) {  // order-preserving compaction of this model's pending starts
       __shared__ int s_cnt;
@@ -166,35 +208,37 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
     tile_step = gridDim.x * (nthr >> 5);
   }
 
-  // ---- stage weights (zero padded) ----
-  for (int l = 0; l < G; ++l) {
-    const int in = d.dims[l], out = d.dims[l + 1];
-    const int in4 = rup(in, 4), outP = rup(out, CH);
-    const float *Wg = params + d.w_off[l];
-    float *wf = smem + P.wf[l];
-    for (int e = tid; e < in4 * outP; e += nthr) {
-      int k = e / outP, j = e - k * outP;
-      wf[e] = (k < in && j < out) ? Wg[k * out + j] : 0.f;
-    }
-    float *bs = smem + P.bias[l];
-    for (int e = tid; e < outP; e += nthr) bs[e] = e < out ? params[d.b_off[l] + e] : 0.f;
-    if (GRAD) {
-      const int out4 = rup(out, 4), inP = rup(in, CH);
-      float *wb = smem + P.wb[l];
-      for (int e = tid; e < out4 * inP; e += nthr) {
-        int j = e / inP, k = e - j * inP;
-        wb[e] = (k < in && j < out) ? Wg[k * out + j] : 0.f;
-      }
+  // ---- stage the pre-packed weight image: one TMA bulk copy (chunks of <= 64 KB) ----
+  if (tid == 0) {
+    const uint32_t bar = smem_addr(&s_bar);
+    const uint32_t total = (uint32_t)P.weights_total * sizeof(float);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
+    for (uint32_t off = 0; off < total; off += 65536u) {
+      const uint32_t nb = total - off < 65536u ? total - off : 65536u;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_addr(smem) + off), "l"(reinterpret_cast<const char *>(packed) + off), "r"(nb),
+                     "r"(bar)
+                   : "memory");
     }
   }
+  __syncthreads();  // the barrier is initialised before anyone polls it
   {
-    const int in = d.dims[G];
-    float *wl = smem + P.wl;
-    for (int e = tid; e < P.wl_len; e += nthr) wl[e] = e < in ? params[d.w_off[G] + e] : 0.f;
+    const uint32_t bar = smem_addr(&s_bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "W_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra W_DONE;\n"
+        "bra W_WAIT;\n"
+        "W_DONE:\n"
+        "}\n" ::"r"(bar)
+        : "memory");
   }
   const float b_last = params[d.b_off[G]];
   const int act_last = d.act[G];
-  __syncthreads();
 
   const int n_tiles = (n + TP - 1) / TP;
   const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
@@ -364,11 +408,35 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
 
 }  // namespace
 
+static int variant_index(bool grad, int UGB) { return (grad ? 2 : 0) + (UGB == 4 ? 1 : 0); }
+
 template <bool GRAD, int UGB>
-static int launch_variant(const bore_mlp *h, const MlpDesc &d, const float *params, const float *X,
+static int pack_variant(const bore_mlp *h, int model0, int n_models, cudaStream_t stream) {
+  using M = Map<UGB>;
+  SmemPlan P;
+  make_plan(h->desc, GRAD, M::CH, M::AST, P);
+  const int v = variant_index(GRAD, UGB);
+  MlpPackCache *pc = h->pack;
+  BORE_CHECK(pc != nullptr, "handle has no pack cache");
+  const size_t need = (size_t)h->n_models * P.weights_total;
+  if (pc->cap[v] < need) {
+    if (pc->buf[v]) BORE_CUDA(cudaFree(pc->buf[v]));
+    pc->buf[v] = nullptr; pc->cap[v] = 0;
+    BORE_CUDA(cudaMalloc(&pc->buf[v], need * sizeof(float)));
+    pc->cap[v] = need;
+  }
+  mlp_pack_kernel<<<n_models, 256, 0, stream>>>(h->desc, P, M::CH, GRAD ? 1 : 0,
+                                                 h->params + (size_t)model0 * h->desc.n_params,
+                                                 pc->buf[v] + (size_t)model0 * P.weights_total);
+  BORE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <bool GRAD, int UGB>
+static int launch_variant(const bore_mlp *h, const MlpDesc &d, int model0, const float *X,
                           int S, float *f, float *g, const int *list, const int *n_dev,
                           int transform, float sign, int n_models, int per_model, const int *flags,
-                          cudaStream_t stream) {
+                          int prepacked, cudaStream_t stream) {
   using M = Map<UGB>;
   SmemPlan P;
   make_plan(d, GRAD, M::CH, M::AST, P);
@@ -378,12 +446,16 @@ static int launch_variant(const bore_mlp *h, const MlpDesc &d, const float *para
   // warps per CTA: as many as fit (<= 16) -- in batched mode no more than the model has tiles
   int warps = 16;
   if (multi) warps = std::min(16, std::max(1, (per_model + M::TP - 1) / M::TP));
-  while (warps > 1 && (size_t)(P.weights_total + warps * P.warp_total) * sizeof(float) + list_bytes + 16 >
+  // 256 B are left for the kernel's static shared memory (mbarrier, counter, alignment)
+  while (warps > 1 && (size_t)(P.weights_total + warps * P.warp_total) * sizeof(float) + list_bytes + 256 >
                           (size_t)max_smem)
     --warps;
   const size_t smem = (size_t)(P.weights_total + warps * P.warp_total) * sizeof(float) + list_bytes;
-  BORE_CHECK(smem + 16 <= (size_t)max_smem, "mlp_eval: model needs %zu B of shared memory (> %d)",
+  BORE_CHECK(smem + 256 <= (size_t)max_smem, "mlp_eval: model needs %zu B of shared memory (> %d)",
              smem, max_smem);
+  if (!prepacked && pack_variant<GRAD, UGB>(h, model0, n_models, stream)) return -1;
+  const float *params = h->params + (size_t)model0 * d.n_params;
+  const float *packed = h->pack->buf[variant_index(GRAD, UGB)] + (size_t)model0 * P.weights_total;
   int grid;
   if (multi) {
     grid = n_models;
@@ -397,44 +469,61 @@ static int launch_variant(const bore_mlp *h, const MlpDesc &d, const float *para
     if (grid > ctas_needed) grid = ctas_needed;
     if (grid < 1) grid = 1;
   }
-  BORE_CUDA(cudaFuncSetAttribute(mlp_eval_kernel<GRAD, UGB>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  mlp_eval_kernel<GRAD, UGB><<<grid, warps * 32, smem, stream>>>(d, P, params, X, S, n_dev, list, f, g,
-                                                               transform, sign, per_model, flags);
+  static bool attr_done[64] = {};  // per device: the attribute belongs to the device's context
+  if (h->device >= 64 || !attr_done[h->device]) {
+    BORE_CUDA(cudaFuncSetAttribute(mlp_eval_kernel<GRAD, UGB>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 256));
+    if (h->device < 64) attr_done[h->device] = true;
+  }
+  mlp_eval_kernel<GRAD, UGB><<<grid, warps * 32, smem, stream>>>(d, P, params, packed, X, S, n_dev, list,
+                                                               f, g, transform, sign, per_model, flags);
   BORE_CUDA(cudaGetLastError());
   return 0;
 }
 
-static int dispatch(const bore_mlp *h, const float *params, bool want_grad, int transform,
-                    int negate, const float *X, int S, float *f, float *g, const int *list,
-                    const int *n_dev, int n_models, int per_model, const int *flags,
-                    cudaStream_t stream) {
-  const MlpDesc &d = h->desc;
+static bool is_wide(const MlpDesc &d) {
   int widest = 0;
   for (int l = 1; l < d.n_layers; ++l) widest = d.dims[l] > widest ? d.dims[l] : widest;
-  const bool wide = widest > 32;  // 64-unit chunks, tiles of 8 points
+  return widest > 32;  // 64-unit chunks, tiles of 8 points
+}
+
+static int dispatch(const bore_mlp *h, int model0, bool want_grad, int transform, int negate,
+                    const float *X, int S, float *f, float *g, const int *list, const int *n_dev,
+                    int n_models, int per_model, const int *flags, int prepacked, cudaStream_t stream) {
+  const MlpDesc &d = h->desc;
+  const bool wide = is_wide(d);
   const float sign = negate ? -1.f : 1.f;
-#define BORE_EVAL(G_, U_) \
-  launch_variant<G_, U_>(h, d, params, X, S, f, g, list, n_dev, transform, sign, n_models, per_model, flags, stream)
+#define BORE_EVAL(G_, U_)                                                                             \
+  launch_variant<G_, U_>(h, d, model0, X, S, f, g, list, n_dev, transform, sign, n_models, per_model, \
+                         flags, prepacked, stream)
   if (want_grad) return wide ? BORE_EVAL(true, 4) : BORE_EVAL(true, 3);
   return wide ? BORE_EVAL(false, 4) : BORE_EVAL(false, 3);
 #undef BORE_EVAL
 }
 
+int mlp_eval_prepare(const bore_mlp *h, int model0, int n_models, bool want_grad, cudaStream_t stream) {
+  const bool wide = is_wide(h->desc);
+  if (want_grad)
+    return wide ? pack_variant<true, 4>(h, model0, n_models, stream)
+                : pack_variant<true, 3>(h, model0, n_models, stream);
+  return wide ? pack_variant<false, 4>(h, model0, n_models, stream)
+              : pack_variant<false, 3>(h, model0, n_models, stream);
+}
+
 int launch_mlp_eval(const bore_mlp *h, int model, bool want_grad, int transform, int negate,
                     const float *X, int S, float *f, float *g, const int *list,
-                    const int *n_dev, cudaStream_t stream) {
+                    const int *n_dev, cudaStream_t stream, int prepacked) {
   if (S <= 0) return 0;
-  return dispatch(h, h->params + (size_t)model * h->desc.n_params, want_grad, transform, negate, X, S,
-                  f, g, list, n_dev, 1, 0, nullptr, stream);
+  return dispatch(h, model, want_grad, transform, negate, X, S, f, g, list, n_dev, 1, 0, nullptr,
+                  prepacked, stream);
 }
 
 // batched problems: model model0+b evaluates points [b*per_model, (b+1)*per_model) of X (those
 // with flags != 0 when `flags` is given), one CTA per model
 int launch_mlp_eval_multi(const bore_mlp *h, int model0, int n_models, int per_model, bool want_grad,
                           int transform, int negate, const float *X, float *f, float *g,
-                          const int *flags, cudaStream_t stream) {
+                          const int *flags, cudaStream_t stream, int prepacked) {
   if (n_models <= 0 || per_model <= 0) return 0;
-  return dispatch(h, h->params + (size_t)model0 * h->desc.n_params, want_grad, transform, negate, X,
-                  n_models * per_model, f, g, nullptr, nullptr, n_models, per_model, flags, stream);
+  return dispatch(h, model0, want_grad, transform, negate, X, n_models * per_model, f, g, nullptr,
+                  nullptr, n_models, per_model, flags, prepacked, stream);
 }
