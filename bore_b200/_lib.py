@@ -32,6 +32,7 @@ SIGNATURES = {
     "bore_mlp_get_adam_state": (C.c_int, [vp, C.c_int, vp, vp, C.POINTER(C.c_int64)]),
     "bore_mlp_reset_optimizer": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "bore_mlp_set_optimizer": (C.c_int, [vp, C.c_float, C.c_float, C.c_float, C.c_float]),
+    "bore_mlp_set_fit_mode": (C.c_int, [vp, C.c_int]),
     "bore_mlp_params_dev": (C.c_int, [vp, C.POINTER(vp)]),
     "bore_mlp_predict": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp]),
     "bore_mlp_value_and_grad": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp]),

@@ -60,6 +60,7 @@ struct bore_mlp {
   long long *adam_t;   // [n_models]   Keras `iterations`
   float lr, beta1, beta2, eps;  // Adam hyper-parameters
   float l2k[BORE_MAX_LAYERS], l2b[BORE_MAX_LAYERS];  // l2 regularisers per layer
+  int fit_mode;  // 0 auto, 1 one CTA per model, 2 one cluster per model (bore_mlp_set_fit_mode)
 };
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }

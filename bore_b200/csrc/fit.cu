@@ -379,6 +379,383 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_kernel(const FitArgs a) {
   if (tid == 0) a.adam_t[model] = t_step;
 }
 
+// ---------------------------------------------------------------- K1c: one model = one CLUSTER
+// A single model on a single CTA is latency bound (~10^3 strictly dependent steps, each a chain
+// of small GEMM tiles on one SM).  fit_cluster_kernel spreads ONE model over a thread-block
+// cluster of FIT_CLUSTER CTAs (= SMs):
+//   * every CTA keeps the full weights (both layouts) in its own shared memory and carries its
+//     slice of the minibatch (ceil(nb / FIT_CLUSTER) samples) through forward / loss / reverse;
+//   * each CTA leaves its partial weight gradient (its samples only) in shared memory, flat in
+//     Keras parameter order; after a cluster barrier CTA r reduces parameter slice r over all
+//     CTAs through distributed shared memory (fixed order 0..C-1: deterministic), applies Adam
+//     with the slots of that slice -- which live in ITS shared memory for the whole run -- and
+//     writes the new weights straight into the W / W^T images of every CTA of the cluster;
+//   * a second cluster barrier, next step.  HBM sees the minibatch gather only.
+// Epoch losses are assembled by rank 0 from per-CTA partial sums (parity slots: a CTA may be
+// one step ahead of rank 0's read).
+constexpr int FIT_CLUSTER = 8;
+
+struct FitCPlan {
+  int w[BORE_MAX_LAYERS], wt[BORE_MAX_LAYERS], b[BORE_MAX_LAYERS];
+  int h[BORE_MAX_LAYERS + 1];  // activations [dim][SP]
+  int dl[2];                   // delta ping/pong [maxw][SP]
+  int zb, red, idx;            // labels [SP], reduction scratch [32], row indices [SP]
+  int dwp;                     // partial gradient, flat [n_params]
+  int am, av;                  // Adam slots of this CTA's parameter slice [chunk]
+  int slots;                   // lsum[2], reg[2]
+  int total, SP, chunk;
+};
+
+__host__ __device__ inline void make_fitc_plan(const MlpDesc &d, int batch, FitCPlan &p) {
+  const int L = d.n_layers;
+  const int SP = r4((batch + FIT_CLUSTER - 1) / FIT_CLUSTER);
+  p.SP = SP;
+  p.chunk = (d.n_params + FIT_CLUSTER - 1) / FIT_CLUSTER;
+  int off = 0, maxw = d.dims[0];
+  for (int l = 0; l < L; ++l) {
+    const int in = d.dims[l], out = d.dims[l + 1];
+    p.w[l] = off; off += in * r4(out);
+    p.b[l] = off; off += r4(out);
+    p.wt[l] = off; if (l > 0) off += out * r4(in);
+    if (out > maxw) maxw = out;
+  }
+  for (int l = 0; l <= L; ++l) { p.h[l] = off; off += d.dims[l] * SP; }
+  p.dl[0] = off; off += maxw * SP;
+  p.dl[1] = off; off += maxw * SP;
+  p.zb = off; off += SP;
+  p.red = off; off += 32;
+  p.idx = off; off += SP;
+  p.dwp = off; off += r4(d.n_params);
+  p.am = off; off += r4(p.chunk);
+  p.av = off; off += r4(p.chunk);
+  p.slots = off; off += 4;
+  p.total = r4(off);
+}
+
+struct FitCArgs {
+  MlpDesc d;
+  FitCPlan P;
+  float *params, *adam_m, *adam_v;
+  long long *adam_t;
+  int model0;
+  const float *X, *z;
+  int N, shared_data, batch, epochs;
+  const int *perm;
+  int shared_perm;
+  float l2k[BORE_MAX_LAYERS], l2b[BORE_MAX_LAYERS];
+  int any_l2;
+  float *loss_out;
+  float lr, beta1, beta2, eps;
+};
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of `p` (a pointer into this CTA's shared memory) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t dsmem_addr(const void *p, uint32_t rank) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(p), r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float dsmem_ld(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void dsmem_st(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+// OUT(j, q) = epi( sum_k A[k][4q..4q+3] * Wm[k*ldw + j] ) for j < nout, q < SP/4.  Consecutive
+// threads take consecutive j (conflict-free weight reads; the activation quad is a broadcast).
+template <class Epi>
+__device__ __forceinline__ void dense_pass(const float *A, const float *Wm, int K, int ldw, int nout,
+                                           int SP, Epi epi) {
+  const int nq = SP >> 2;
+  for (int o = threadIdx.x; o < nout * nq; o += blockDim.x) {
+    const int q = o / nout, j = o - q * nout;
+    const float *ap = A + 4 * q;
+    const float *wp = Wm + j;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+      const float4 a = *reinterpret_cast<const float4 *>(ap + k * SP);
+      const float w = wp[k * ldw];
+      acc.x = fmaf(a.x, w, acc.x);
+      acc.y = fmaf(a.y, w, acc.y);
+      acc.z = fmaf(a.z, w, acc.z);
+      acc.w = fmaf(a.w, w, acc.w);
+    }
+    epi(j, q, acc);
+  }
+}
+
+__global__ void __cluster_dims__(FIT_CLUSTER, 1, 1) __launch_bounds__(FIT_THREADS)
+fit_cluster_kernel(const FitCArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const MlpDesc &d = a.d;
+  const FitCPlan &P = a.P;
+  const int L = d.n_layers, SP = P.SP;
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const int rank = (int)cluster_rank();
+  const int cl = blockIdx.x / FIT_CLUSTER;  // which model of the launch
+  const int model = a.model0 + cl;
+  float *gp = a.params + (size_t)model * d.n_params;
+  float *gm = a.adam_m + (size_t)model * d.n_params;
+  float *gv = a.adam_v + (size_t)model * d.n_params;
+  const float *X = a.X + (a.shared_data ? 0 : (size_t)cl * a.N * d.dims[0]);
+  const float *zg = a.z + (a.shared_data ? 0 : (size_t)cl * a.N);
+  const int *perm = a.perm + (a.shared_perm ? 0 : (size_t)cl * a.epochs * a.N);
+  int *idxb = reinterpret_cast<int *>(sm + P.idx);
+  float *red = sm + P.red;
+  const int D = d.dims[0];
+  const int i0 = rank * P.chunk;                       // this CTA's parameter slice
+  const int i1 = min(i0 + P.chunk, d.n_params);
+
+  // ---- stage the weights (all CTAs) and this CTA's Adam slots ----
+  for (int l = 0; l < L; ++l) {
+    const int in = d.dims[l], out = d.dims[l + 1], JP = r4(out), KP = r4(in);
+    for (int e = tid; e < in * JP; e += NT) {
+      const int k = e / JP, j = e - k * JP;
+      sm[P.w[l] + e] = j < out ? gp[d.w_off[l] + k * out + j] : 0.f;
+    }
+    for (int e = tid; e < JP; e += NT) sm[P.b[l] + e] = e < out ? gp[d.b_off[l] + e] : 0.f;
+    if (l > 0)
+      for (int e = tid; e < out * KP; e += NT) {
+        const int j = e / KP, k = e - j * KP;
+        sm[P.wt[l] + e] = k < in ? gp[d.w_off[l] + k * out + j] : 0.f;
+      }
+  }
+  for (int i = i0 + tid; i < i1; i += NT) {
+    sm[P.am + i - i0] = gm[i];
+    sm[P.av + i - i0] = gv[i];
+  }
+  if (tid < 4) sm[P.slots + tid] = 0.f;
+  long long t_step = a.adam_t[model];
+  cluster_sync_all();  // everybody's shared memory exists and is initialised
+
+  const int steps_per_epoch = (a.N + a.batch - 1) / a.batch;
+  int par = 0;  // slot parity of the current step
+  for (int ep = 0; ep < a.epochs; ++ep) {
+    float epoch_tot = 0.f;
+    for (int st = 0; st < steps_per_epoch; ++st, par ^= 1) {
+      const int s0 = st * a.batch;
+      const int nb = min(a.batch, a.N - s0);
+      const int spc = (nb + FIT_CLUSTER - 1) / FIT_CLUSTER;  // samples per CTA
+      const int p0 = rank * spc;
+      const int mine = max(0, min(spc, nb - p0));             // this CTA's samples
+      // ---- gather this CTA's slice of the minibatch (transposed, zero padded) ----
+      for (int p = tid; p < SP; p += NT) {
+        const int row = p < mine ? perm[(size_t)ep * a.N + s0 + p0 + p] : -1;
+        idxb[p] = row;
+        sm[P.zb + p] = row >= 0 ? zg[row] : 0.f;
+      }
+      __syncthreads();
+      for (int e = tid; e < SP * D; e += NT) {
+        const int p = e / D, k = e - p * D;
+        const int row = idxb[p];
+        sm[P.h[0] + k * SP + p] = row >= 0 ? X[(size_t)row * D + k] : 0.f;
+      }
+      __syncthreads();
+
+      // ---- forward ----
+      for (int l = 0; l < L; ++l) {
+        const int in = d.dims[l], out = d.dims[l + 1], JP = r4(out);
+        const float *bs = sm + P.b[l];
+        float *H = sm + P.h[l + 1];
+        const int act = (l == L - 1) ? BORE_ACT_LINEAR : d.act[l];  // loss works on the logit
+        dense_pass(sm + P.h[l], sm + P.w[l], in, JP, out, SP, [&](int j, int q, float4 acc) {
+          const float b = bs[j];
+          float4 o;
+          o.x = f_act(act, acc.x + b);
+          o.y = f_act(act, acc.y + b);
+          o.z = f_act(act, acc.z + b);
+          o.w = f_act(act, acc.w + b);
+          *reinterpret_cast<float4 *>(H + j * SP + 4 * q) = o;
+        });
+        __syncthreads();
+      }
+
+      // ---- loss (partial sum over this CTA's samples) and dL/dlogit (mean over the batch) ----
+      const float inv_nb = 1.f / (float)nb;
+      float lsum = 0.f;
+      {
+        const float *U = sm + P.h[L];
+        float *dz = sm + P.dl[0];
+        for (int p = tid; p < SP; p += NT) {
+          float dl = 0.f;
+          if (p < mine) {
+            const float u = U[p], zz = sm[P.zb + p];
+            lsum += fmaxf(u, 0.f) - u * zz + log1pf(expf(-fabsf(u)));
+            dl = (stable_sigmoid(u) - zz) * inv_nb;
+          }
+          dz[p] = dl;
+        }
+      }
+      lsum = block_sum(lsum, red);  // (also the barrier publishing dz)
+      if (tid == 0) sm[P.slots + par] = lsum;
+
+      // ---- Adam scalars for this step (Keras: t starts at 1) ----
+      t_step += 1;
+      const float b1p = powf(a.beta1, (float)t_step), b2p = powf(a.beta2, (float)t_step);
+      const float alpha = a.lr * sqrtf(1.f - b2p) / (1.f - b1p);
+      const float om1 = 1.f - a.beta1, om2 = 1.f - a.beta2;
+
+      // ---- reverse: per layer, delta_{l-1} and this CTA's partial dW_l / db_l ----
+      int cur = 0;
+      for (int l = L - 1; l >= 0; --l) {
+        const int in = d.dims[l], out = d.dims[l + 1], KP = r4(in);
+        const float *DL = sm + P.dl[cur];  // delta_l [out][SP]
+        const float *Hin = sm + P.h[l];
+        if (l > 0) {
+          float *DN = sm + P.dl[cur ^ 1];
+          const int actp = d.act[l - 1];
+          dense_pass(DL, sm + P.wt[l], out, KP, in, SP, [&](int k, int q, float4 acc) {
+            const float4 hv = *reinterpret_cast<const float4 *>(Hin + k * SP + 4 * q);
+            float4 o;
+            o.x = acc.x * f_act_bwd(actp, hv.x);
+            o.y = acc.y * f_act_bwd(actp, hv.y);
+            o.z = acc.z * f_act_bwd(actp, hv.z);
+            o.w = acc.w * f_act_bwd(actp, hv.w);
+            *reinterpret_cast<float4 *>(DN + k * SP + 4 * q) = o;
+          });
+        }
+        {
+          // partial dW_l = h_{l-1}^T delta_l over this CTA's samples: 4(k) x 4(j) register tiles
+          float *dW = sm + P.dwp + d.w_off[l];
+          const int tkn = (in + 3) / 4, tjn = (out + 3) / 4;
+          for (int tt = tid; tt < tkn * tjn; tt += NT) {
+            const int tk = tt % tkn, tj = tt / tkn;
+            float acc[4][4] = {};
+            int kk[4], jj[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              kk[u] = min(tk + u * tkn, in - 1);
+              jj[u] = min(tj * 4 + u, out - 1);
+            }
+            for (int p = 0; p < SP; p += 4) {
+              float4 hv[4], dv[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                hv[u] = *reinterpret_cast<const float4 *>(Hin + kk[u] * SP + p);
+                dv[u] = *reinterpret_cast<const float4 *>(DL + jj[u] * SP + p);
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  acc[i][u] = fmaf(hv[i].x, dv[u].x, acc[i][u]);
+                  acc[i][u] = fmaf(hv[i].y, dv[u].y, acc[i][u]);
+                  acc[i][u] = fmaf(hv[i].z, dv[u].z, acc[i][u]);
+                  acc[i][u] = fmaf(hv[i].w, dv[u].w, acc[i][u]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int k = tk + i * tkn;
+              if (k >= in) continue;
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int j = tj * 4 + u;
+                if (j < out) dW[k * out + j] = acc[i][u];
+              }
+            }
+          }
+          float *dB = sm + P.dwp + d.b_off[l];
+          for (int j = tid; j < out; j += NT) {
+            float g = 0.f;
+            for (int p = 0; p < SP; ++p) g += DL[j * SP + p];
+            dB[j] = g;
+          }
+        }
+        __syncthreads();
+        cur ^= 1;
+      }
+
+      cluster_sync_all();  // every CTA's partial gradient is complete
+
+      // ---- reduce slice `rank` over the cluster, Adam, scatter the new weights to every CTA ----
+      float reg = 0.f;
+      for (int i = i0 + tid; i < i1; i += NT) {
+        float g = 0.f;
+#pragma unroll
+        for (int c = 0; c < FIT_CLUSTER; ++c) g += dsmem_ld(dsmem_addr(sm + P.dwp + i, c));
+        // which parameter is flat index i?
+        int l = 0;
+        while (l + 1 < L && i >= d.w_off[l + 1]) ++l;
+        const int in = d.dims[l], out = d.dims[l + 1];
+        const bool is_bias = i >= d.b_off[l];
+        int off_w, off_wt = -1;
+        float l2;
+        if (is_bias) {
+          off_w = P.b[l] + (i - d.b_off[l]);
+          l2 = a.l2b[l];
+        } else {
+          const int e = i - d.w_off[l], k = e / out, j = e - k * out;
+          off_w = P.w[l] + k * r4(out) + j;
+          if (l > 0) off_wt = P.wt[l] + j * r4(in) + k;
+          l2 = a.l2k[l];
+        }
+        float wv = sm[off_w];
+        if (l2 != 0.f) { reg += l2 * wv * wv; g += 2.f * l2 * wv; }
+        float m = sm[P.am + i - i0], v = sm[P.av + i - i0];
+        m += (g - m) * om1;
+        v += (g * g - v) * om2;
+        wv -= (m * alpha) / (sqrtf(v) + a.eps);
+        sm[P.am + i - i0] = m;
+        sm[P.av + i - i0] = v;
+#pragma unroll
+        for (int c = 0; c < FIT_CLUSTER; ++c) {
+          dsmem_st(dsmem_addr(sm + off_w, c), wv);
+          if (off_wt >= 0) dsmem_st(dsmem_addr(sm + off_wt, c), wv);
+        }
+      }
+      if (a.any_l2) {
+        reg = block_sum(reg, red);
+        if (tid == 0) sm[P.slots + 2 + par] = reg;
+      }
+
+      cluster_sync_all();  // new weights everywhere; loss / reg slots of this step published
+
+      if (rank == 0 && tid == 0) {
+        float ls = 0.f, rg = 0.f;
+        for (int c = 0; c < FIT_CLUSTER; ++c) {
+          ls += dsmem_ld(dsmem_addr(sm + P.slots + par, c));
+          if (a.any_l2) rg += dsmem_ld(dsmem_addr(sm + P.slots + 2 + par, c));
+        }
+        epoch_tot += (ls * inv_nb + rg) * (float)nb;
+      }
+    }
+    if (rank == 0 && tid == 0 && a.loss_out)
+      a.loss_out[(size_t)cl * a.epochs + ep] = epoch_tot / (float)a.N;
+  }
+
+  // ---- write back: rank 0 the weights, every CTA its Adam slice ----
+  __syncthreads();
+  if (rank == 0) {
+    for (int l = 0; l < L; ++l) {
+      const int in = d.dims[l], out = d.dims[l + 1], JP = r4(out);
+      for (int e = tid; e < in * out; e += NT) {
+        const int k = e / out, j = e - k * out;
+        gp[d.w_off[l] + e] = sm[P.w[l] + k * JP + j];
+      }
+      for (int e = tid; e < out; e += NT) gp[d.b_off[l] + e] = sm[P.b[l] + e];
+    }
+    if (tid == 0) a.adam_t[model] = t_step;
+  }
+  for (int i = i0 + tid; i < i1; i += NT) {
+    gm[i] = sm[P.am + i - i0];
+    gv[i] = sm[P.av + i - i0];
+  }
+  cluster_sync_all();  // nobody exits while a peer may still read its shared memory
+}
+
 // ---------------------------------------------------------------- evaluate (loss, accuracy)
 __global__ void __launch_bounds__(256)
 evaluate_kernel(const MlpDesc d, const float *__restrict__ params, const float *__restrict__ logits,
@@ -444,9 +821,41 @@ int bore_mlp_fit(bore_mlp *h, int model0, int count, const float *X_dev, const f
   }
   a.loss_out = loss_out_dev;
   a.lr = h->lr; a.beta1 = h->beta1; a.beta2 = h->beta2; a.eps = h->eps;
+  // Few models: one thread-block cluster (8 SMs) per model -- the run is latency bound and a
+  // single CTA leaves the other 147 SMs idle.  Many models: one CTA each fills the GPU already.
+  {
+    FitCPlan CP;
+    make_fitc_plan(a.d, B, CP);
+    const size_t csmem = (size_t)CP.total * sizeof(float);
+    const bool fits = csmem <= 200 * 1024;
+    const bool want = h->fit_mode == 2 || (h->fit_mode == 0 && count * FIT_CLUSTER <= h->sm_count);
+    BORE_CHECK(!(h->fit_mode == 2 && !fits), "bore_mlp_fit: cluster mode needs %zu B of shared memory", csmem);
+    if (want && fits) {
+      FitCArgs c;
+      c.d = a.d; c.P = CP;
+      c.params = a.params; c.adam_m = a.adam_m; c.adam_v = a.adam_v; c.adam_t = a.adam_t;
+      c.model0 = a.model0; c.X = a.X; c.z = a.z; c.N = a.N; c.shared_data = a.shared_data;
+      c.batch = a.batch; c.epochs = a.epochs; c.perm = a.perm; c.shared_perm = a.shared_perm;
+      for (int l = 0; l < BORE_MAX_LAYERS; ++l) { c.l2k[l] = a.l2k[l]; c.l2b[l] = a.l2b[l]; }
+      c.any_l2 = a.any_l2; c.loss_out = a.loss_out;
+      c.lr = a.lr; c.beta1 = a.beta1; c.beta2 = a.beta2; c.eps = a.eps;
+      BORE_CUDA(cudaFuncSetAttribute(fit_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)csmem));
+      fit_cluster_kernel<<<count * FIT_CLUSTER, FIT_THREADS, csmem, (cudaStream_t)stream>>>(c);
+      BORE_CUDA(cudaGetLastError());
+      return 0;
+    }
+  }
   BORE_CUDA(cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   fit_kernel<<<count, FIT_THREADS, smem, (cudaStream_t)stream>>>(a);
   BORE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bore_mlp_set_fit_mode(bore_mlp *h, int mode) {
+  BORE_CHECK(h != nullptr, "NULL handle");
+  BORE_CHECK(mode >= 0 && mode <= 2, "bore_mlp_set_fit_mode: mode %d outside [0,2]", mode);
+  h->fit_mode = mode;
   return 0;
 }
 

@@ -175,14 +175,8 @@ LB_FN void lb_carve(LbWork &w, double *dbase, int *ibase, int n, int m) {
 // 0 ok, else k+1.  Right-looking: after column k is scaled, lane j owns column k+1+j of the
 // trailing block and walks its rows, so there is no index arithmetic in the inner loop.
 #if LB_WARP
-// sqrt(a) and 1/sqrt(a); one copy of the two (long) fp64 sequences for the unrolled callers
-struct LbRoots { double root, rinv; };
-LB_NI LbRoots lb_roots(double a) {
-  LbRoots r;
-  r.root = sqrt(a);
-  r.rinv = rsqrt(a);
-  return r;
-}
+// 1/sqrt(a); one copy of the (long) fp64 sequence for the unrolled caller
+LB_NI double lb_rsqrt(double a) { return rsqrt(a); }
 #endif
 LB_NI int lb_chol(double *A, int ld, int n, double *rd) {
   LB_SHARED(A); LB_SHARED(rd);
@@ -205,10 +199,13 @@ LB_NI int lb_chol(double *A, int ld, int n, double *rd) {
   for (int k = 0; k < LB_MMAX; ++k) {
     const double akk = __shfl_sync(0xffffffffu, a[k], k);
     if (!(akk > 0.0)) return k + 1;
-    const LbRoots rt = lb_roots(akk);
-    const double akj = a[k] * rt.rinv;
-    a[k] = j == k ? rt.root : akj;
-    if (j == k && k < n) rd[k] = rt.rinv;
+    // the factor's diagonal is only ever used through its reciprocal (rd): every consumer on
+    // the device (lb_trsl_*, formt's inverse, formk's forward substitution) multiplies by rd[k],
+    // so sqrt(akk) itself is not formed; the diagonal slot keeps akk * rinv
+    const double rinv = lb_rsqrt(akk);
+    const double akj = a[k] * rinv;
+    a[k] = akj;
+    if (j == k && k < n) rd[k] = rinv;
 #pragma unroll
     for (int i = k + 1; i < LB_MMAX; ++i) a[i] -= __shfl_sync(0xffffffffu, akj, i) * akj;  // lane i holds R[k][i]
   }

@@ -103,15 +103,37 @@ class NativeMLP:
         return out
 
     def to_device(self, a, dtype):
-        """numpy -> device tensor through a pinned staging buffer."""
+        """numpy -> device tensor through a cached pinned staging buffer (page-locking a fresh
+        buffer per call costs more than the copy itself).  A buffer is reused once the event
+        recorded behind its last host-to-device copy has completed."""
         torch = _torch()
         a = np.ascontiguousarray(a, dtype=dtype)
-        t = torch.from_numpy(a)
-        try:
-            t = t.pin_memory()
-        except RuntimeError:
-            pass
-        return t.to(self._tdev(), non_blocking=True)
+        tdt = torch.from_numpy(a[:0].reshape(-1)).dtype
+        if a.nbytes == 0:
+            return torch.empty(a.shape, dtype=tdt, device=self._tdev())
+        pool = self.__dict__.setdefault("_pinned", [])
+        best = None
+        for ent in pool:
+            if ent[0].numel() >= a.nbytes and ent[1].query() and (best is None or ent[0].numel() < best[0].numel()):
+                best = ent
+        if best is None:
+            cap = 1 << max(12, int(a.nbytes - 1).bit_length())
+            try:
+                buf = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+            except RuntimeError:
+                return torch.from_numpy(a).to(self._tdev())
+            best = [buf, torch.cuda.Event()]
+            pool.append(best)
+            if len(pool) > 16:  # drop the oldest idle buffer
+                for i, ent in enumerate(pool[:-1]):
+                    if ent[1].query():
+                        del pool[i]
+                        break
+        view = best[0][:a.nbytes].view(tdt).reshape(a.shape)
+        view.numpy()[...] = a
+        out = view.to(self._tdev(), non_blocking=True)
+        best[1].record(torch.cuda.current_stream(self.device))
+        return out
 
     # ------------------------------------------------------------------ parameters
     def set_weights(self, weights, model=0):
@@ -143,6 +165,10 @@ class NativeMLP:
 
     def set_optimizer(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7):
         _lib.check(self.lib.bore_mlp_set_optimizer(self.h, lr, beta1, beta2, eps))
+
+    def set_fit_mode(self, mode):
+        """0 automatic, 1 one CTA per model, 2 one thread-block cluster per model."""
+        _lib.check(self.lib.bore_mlp_set_fit_mode(self.h, int(mode)))
 
     def set_regularizers(self, l2):
         """``l2``: one factor for every kernel and bias, or a per-array sequence in Keras weight
@@ -345,11 +371,21 @@ class NativeMLP:
         X = np.asarray(X)
         N = X.shape[0]
         perm = np.ascontiguousarray(permutations, np.int32).reshape(epochs, N)
-        loss = self.fit_dev(self.to_device(X, np.float32),
+        return self.fit_async(X, z, epochs, batch_size, perm, model=model).cpu().numpy()[0]
+
+    def fit_async(self, X, z, epochs, batch_size, permutations, l2=None, model=0):
+        """Like ``fit`` but returns the (1, epochs) device tensor of epoch losses without waiting
+        for the training kernel: the host is free (e.g. to draw the start points of the next
+        argmax) while the GPU trains."""
+        if l2 is not None:
+            self.set_regularizers(l2)
+        X = np.asarray(X)
+        N = X.shape[0]
+        perm = np.ascontiguousarray(permutations, np.int32).reshape(epochs, N)
+        return self.fit_dev(self.to_device(X, np.float32),
                             self.to_device(np.asarray(z).astype(np.float32), np.float32),
                             N, batch_size, epochs, self.to_device(perm, np.int32),
                             model0=model, count=1)
-        return loss.cpu().numpy()[0]
 
     def evaluate(self, X, z, l2=None, model=0):
         if l2 is not None:

@@ -17,9 +17,22 @@ from .mixins import MaximizableMixin
 
 
 class History:
-    def __init__(self, loss):
-        self.history = {"loss": [float(v) for v in loss]}
-        self.epoch = list(range(len(loss)))
+    """``history["loss"]`` like Keras' History.  ``loss`` may be a zero-argument callable: the
+    training kernel is launched asynchronously and the epoch losses are fetched from the device
+    the first time ``history`` is read, so ``fit`` does not stall the host."""
+
+    def __init__(self, loss, epochs=None):
+        self._loss = loss
+        self._history = None
+        self.epoch = list(range(len(loss) if epochs is None else epochs))
+
+    @property
+    def history(self):
+        if self._history is None:
+            loss = self._loss() if callable(self._loss) else self._loss
+            self._history = {"loss": [float(v) for v in loss]}
+            self._loss = None
+        return self._history
 
 
 class Sequential:
@@ -173,11 +186,13 @@ class Sequential:
                 permutations = np.stack([self._rs.permutation(N) for _ in range(epochs)])
             else:
                 permutations = np.tile(np.arange(N), (epochs, 1))
-        loss = net.fit(X, z, epochs, batch_size, permutations, l2=self._l2())
+        loss_dev = net.fit_async(X, z, epochs, batch_size, permutations, l2=self._l2())
+        hist = History(lambda: loss_dev.cpu().numpy()[0], epochs)
         if verbose:
+            loss = hist.history["loss"]
             print(f"fit: {epochs} epochs x {-(-N // batch_size)} steps, "
                   f"loss {loss[0]:.4f} -> {loss[-1]:.4f}")
-        return History(loss)
+        return hist
 
     def predict(self, x, **kwargs):
         X = np.asarray(x)

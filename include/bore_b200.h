@@ -115,6 +115,13 @@ int bore_mlp_fit(bore_mlp *h, int model0, int count, const float *X_dev,
                  const float *z_dev, int N, int shared_data, int batch_size, int epochs,
                  const int32_t *perm_dev, int shared_perm, float *loss_out_dev, void *stream);
 
+/* How bore_mlp_fit maps models onto the GPU: 0 = automatic (default), 1 = one CTA per model
+ * (throughput mode, many concurrent models), 2 = one 8-CTA thread-block cluster per model
+ * (latency mode: the minibatch is split over 8 SMs, gradients meet in distributed shared
+ * memory).  Automatic picks 2 while 8 * count <= number of SMs.  Same results up to fp32
+ * summation order.                                                                        */
+int bore_mlp_set_fit_mode(bore_mlp *h, int mode);
+
 /* Keras Model.evaluate -> mean loss and `accuracy` (plugins/hpbandster/base.py:186).
  * out_host[0]=loss, out_host[1]=accuracy.  synchronous.                                 */
 int bore_mlp_evaluate(bore_mlp *h, int model, const float *X_dev, const float *z_dev,

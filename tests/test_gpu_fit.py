@@ -38,8 +38,10 @@ CASES = [
 ]
 
 
+# fit modes (bore_mlp_set_fit_mode): 1 = one CTA per model, 2 = one 8-CTA cluster per model
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("name,N,epochs,batch,l2", CASES)
-def test_fit_loss_trajectory_matches_oracle(name, N, epochs, batch, l2):
+def test_fit_loss_trajectory_matches_oracle(name, N, epochs, batch, l2, mode):
     from bore_b200.engine import NativeMLP
     dims, acts, _ = NETS[name]
     X, z, perms = _problem(dims, N, epochs, seed=N + epochs)
@@ -49,6 +51,7 @@ def test_fit_loss_trajectory_matches_oracle(name, N, epochs, batch, l2):
     hist_ref, adam_ref = km.fit(w_ref, acts, X, z, epochs, batch, perms, l2=l2)
 
     net = NativeMLP(dims, acts)
+    net.set_fit_mode(mode)
     net.set_weights(w0)
     hist = net.fit(X, z, epochs, batch, perms, l2=l2)
     assert hist.shape == (epochs,)
