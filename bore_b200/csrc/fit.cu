@@ -385,49 +385,63 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_kernel(const FitArgs a) {
 // cluster of FIT_CLUSTER CTAs (= SMs):
 //   * every CTA keeps the full weights (both layouts) in its own shared memory and carries its
 //     slice of the minibatch (ceil(nb / FIT_CLUSTER) samples) through forward / loss / reverse;
-//   * each CTA leaves its partial weight gradient (its samples only) in shared memory, flat in
-//     Keras parameter order; after a cluster barrier CTA r reduces parameter slice r over all
-//     CTAs through distributed shared memory (fixed order 0..C-1: deterministic), applies Adam
-//     with the slots of that slice -- which live in ITS shared memory for the whole run -- and
-//     writes the new weights straight into the W / W^T images of every CTA of the cluster;
-//   * a second cluster barrier, next step.  HBM sees the minibatch gather only.
-// Epoch losses are assembled by rank 0 from per-CTA partial sums (parity slots: a CTA may be
-// one step ahead of rank 0's read).
+//     the k-loop of every output is split over 2..8 adjacent lanes (shuffle-reduced) so that all
+//     256 threads share the few hundred outputs of a layer;
+//   * each CTA leaves its partial gradient (its samples only) in shared memory, flat in Keras
+//     parameter order; after a cluster barrier CTA r reduces parameter slice r over all CTAs
+//     through distributed shared memory (float4 loads, fixed order 0..C-1: deterministic),
+//     applies Adam with the slots of that slice -- which live in ITS shared memory for the whole
+//     run -- and leaves the new values in place of its own partial slice;
+//   * after a second cluster barrier (the next minibatch is gathered between its arrive and its
+//     wait) every CTA pulls the updated slices from their owners and rewrites its W / W^T images.
+// HBM sees the minibatch gather only.  Epoch losses are assembled by rank 0 from per-CTA
+// partial sums (parity slots: a CTA may be one step ahead of rank 0's read).
 constexpr int FIT_CLUSTER = 8;
+constexpr int FIT_CTHREADS = 512;  // threads per CTA of the cluster kernel
 
 struct FitCPlan {
   int w[BORE_MAX_LAYERS], wt[BORE_MAX_LAYERS], b[BORE_MAX_LAYERS];
   int h[BORE_MAX_LAYERS + 1];  // activations [dim][SP]
   int dl[2];                   // delta ping/pong [maxw][SP]
   int zb, red, idx;            // labels [SP], reduction scratch [32], row indices [SP]
-  int dwp;                     // partial gradient, flat [n_params]
+  int dwp;                     // partial gradient, flat [FIT_CLUSTER * chunk]
+  int wn;                      // updated values of this CTA's parameter slice [chunk]
   int am, av;                  // Adam slots of this CTA's parameter slice [chunk]
+  int tab;                     // flat index -> (offset in W/bias image) | (offset in W^T image + 1) << 16
   int slots;                   // lsum[2], reg[2]
-  int total, SP, chunk;
+  int total, SP, chunk, wend;  // wend: end of the weight images (offsets must fit 16 bits)
 };
+
+// leading dimensions of the weight images: odd, so that lanes reading one column at different
+// rows (the k-split of dense_pass) hit different banks
+__host__ __device__ inline int ldo(int n) { return r4(n) + 1; }
 
 __host__ __device__ inline void make_fitc_plan(const MlpDesc &d, int batch, FitCPlan &p) {
   const int L = d.n_layers;
   const int SP = r4((batch + FIT_CLUSTER - 1) / FIT_CLUSTER);
   p.SP = SP;
-  p.chunk = (d.n_params + FIT_CLUSTER - 1) / FIT_CLUSTER;
+  p.chunk = r4((d.n_params + FIT_CLUSTER - 1) / FIT_CLUSTER);
   int off = 0, maxw = d.dims[0];
   for (int l = 0; l < L; ++l) {
     const int in = d.dims[l], out = d.dims[l + 1];
-    p.w[l] = off; off += in * r4(out);
+    p.w[l] = off; off += in * ldo(out);
     p.b[l] = off; off += r4(out);
-    p.wt[l] = off; if (l > 0) off += out * r4(in);
+    p.wt[l] = off; if (l > 0) off += out * ldo(in);
     if (out > maxw) maxw = out;
   }
+  off = r4(off);
+  p.wend = off;
   for (int l = 0; l <= L; ++l) { p.h[l] = off; off += d.dims[l] * SP; }
   p.dl[0] = off; off += maxw * SP;
   p.dl[1] = off; off += maxw * SP;
   p.zb = off; off += SP;
   p.red = off; off += 32;
   p.idx = off; off += SP;
-  p.dwp = off; off += r4(d.n_params);
-  p.am = off; off += r4(p.chunk);
-  p.av = off; off += r4(p.chunk);
+  p.dwp = off; off += FIT_CLUSTER * p.chunk;
+  p.wn = off; off += p.chunk;
+  p.am = off; off += p.chunk;
+  p.av = off; off += p.chunk;
+  p.tab = off; off += FIT_CLUSTER * p.chunk;
   p.slots = off; off += 4;
   p.total = r4(off);
 }
@@ -453,9 +467,11 @@ __device__ __forceinline__ uint32_t cluster_rank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n"
-               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+__device__ __forceinline__ void cluster_arrive() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // address of `p` (a pointer into this CTA's shared memory) in CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t dsmem_addr(const void *p, uint32_t rank) {
@@ -468,23 +484,37 @@ __device__ __forceinline__ float dsmem_ld(uint32_t addr) {
   asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
   return v;
 }
-__device__ __forceinline__ void dsmem_st(uint32_t addr, float v) {
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+__device__ __forceinline__ float4 dsmem_ld4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr)
+               : "memory");
+  return v;
 }
 
-// OUT(j, q) = epi( sum_k A[k][4q..4q+3] * Wm[k*ldw + j] ) for j < nout, q < SP/4.  Consecutive
-// threads take consecutive j (conflict-free weight reads; the activation quad is a broadcast).
+// OUT(j, q) = epi( sum_k A[k][4q..4q+3] * Wm[k*ldw + j] ) for j < nout, q < SP/4.  An output is
+// shared by `ks` adjacent lanes (k interleaved, partial sums combined by shuffle); `ks` is the
+// largest power of two <= 8 that still leaves every thread an output.  ldw is odd (ldo).
 template <class Epi>
 __device__ __forceinline__ void dense_pass(const float *A, const float *Wm, int K, int ldw, int nout,
                                            int SP, Epi epi) {
-  const int nq = SP >> 2;
-  for (int o = threadIdx.x; o < nout * nq; o += blockDim.x) {
-    const int q = o / nout, j = o - q * nout;
+  const int nq = SP >> 2, items = nout * nq, NT = blockDim.x;
+  int ksh = 0;
+  while (ksh < 3 && (items << (ksh + 1)) <= NT) ++ksh;
+  const int ks = 1 << ksh;
+  const int kp = threadIdx.x & (ks - 1);
+  const int per_pass = NT >> ksh;
+  for (int base = 0; base < items; base += per_pass) {
+    const int o = base + (threadIdx.x >> ksh);
+    const bool valid = o < items;
+    const int oo = valid ? o : 0;
+    const int q = oo / nout, j = oo - q * nout;
     const float *ap = A + 4 * q;
     const float *wp = Wm + j;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-    for (int k = 0; k < K; ++k) {
+    for (int k = kp; k < K; k += ks) {
       const float4 a = *reinterpret_cast<const float4 *>(ap + k * SP);
       const float w = wp[k * ldw];
       acc.x = fmaf(a.x, w, acc.x);
@@ -492,11 +522,17 @@ __device__ __forceinline__ void dense_pass(const float *A, const float *Wm, int 
       acc.z = fmaf(a.z, w, acc.z);
       acc.w = fmaf(a.w, w, acc.w);
     }
-    epi(j, q, acc);
+    for (int off = ks >> 1; off > 0; off >>= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
+      acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
+    }
+    if (valid && kp == 0) epi(j, q, acc);
   }
 }
 
-__global__ void __cluster_dims__(FIT_CLUSTER, 1, 1) __launch_bounds__(FIT_THREADS)
+__global__ void __cluster_dims__(FIT_CLUSTER, 1, 1) __launch_bounds__(FIT_CTHREADS)
 fit_cluster_kernel(const FitCArgs a) {
   extern __shared__ __align__(16) float sm[];
   const MlpDesc &d = a.d;
@@ -517,30 +553,84 @@ fit_cluster_kernel(const FitCArgs a) {
   const int D = d.dims[0];
   const int i0 = rank * P.chunk;                       // this CTA's parameter slice
   const int i1 = min(i0 + P.chunk, d.n_params);
+  const int steps_per_epoch = (a.N + a.batch - 1) / a.batch;
+
+  // gathers this CTA's slice of minibatch (ep, st), transposed and zero padded; ends published
+  auto gather = [&](int ep, int st) {
+    const int s0 = st * a.batch;
+    const int nb = min(a.batch, a.N - s0);
+    const int spc = (nb + FIT_CLUSTER - 1) / FIT_CLUSTER;
+    const int p0 = rank * spc;
+    const int mine = max(0, min(spc, nb - p0));
+    for (int p = tid; p < SP; p += NT) {
+      const int row = p < mine ? perm[(size_t)ep * a.N + s0 + p0 + p] : -1;
+      idxb[p] = row;
+      sm[P.zb + p] = row >= 0 ? zg[row] : 0.f;
+    }
+    __syncthreads();
+    for (int e = tid; e < SP * D; e += NT) {
+      const int p = e / D, k = e - p * D;
+      const int row = idxb[p];
+      sm[P.h[0] + k * SP + p] = row >= 0 ? X[(size_t)row * D + k] : 0.f;
+    }
+    __syncthreads();
+  };
+  // flat parameter index -> offsets of that parameter in the W (or bias) and W^T images
+  auto locate = [&](int i, int &off_w, int &off_wt, float &l2) {
+    int l = 0;
+    while (l + 1 < L && i >= d.w_off[l + 1]) ++l;
+    const int in = d.dims[l], out = d.dims[l + 1];
+    off_wt = -1;
+    if (i >= d.b_off[l]) {
+      off_w = P.b[l] + (i - d.b_off[l]);
+      l2 = a.l2b[l];
+    } else {
+      const int e = i - d.w_off[l], k = e / out, j = e - k * out;
+      off_w = P.w[l] + k * ldo(out) + j;
+      if (l > 0) off_wt = P.wt[l] + j * ldo(in) + k;
+      l2 = a.l2k[l];
+    }
+  };
 
   // ---- stage the weights (all CTAs) and this CTA's Adam slots ----
   for (int l = 0; l < L; ++l) {
-    const int in = d.dims[l], out = d.dims[l + 1], JP = r4(out), KP = r4(in);
+    const int in = d.dims[l], out = d.dims[l + 1], JP = ldo(out), KP = ldo(in);
     for (int e = tid; e < in * JP; e += NT) {
       const int k = e / JP, j = e - k * JP;
       sm[P.w[l] + e] = j < out ? gp[d.w_off[l] + k * out + j] : 0.f;
     }
-    for (int e = tid; e < JP; e += NT) sm[P.b[l] + e] = e < out ? gp[d.b_off[l] + e] : 0.f;
+    for (int e = tid; e < r4(out); e += NT) sm[P.b[l] + e] = e < out ? gp[d.b_off[l] + e] : 0.f;
     if (l > 0)
       for (int e = tid; e < out * KP; e += NT) {
         const int j = e / KP, k = e - j * KP;
         sm[P.wt[l] + e] = k < in ? gp[d.w_off[l] + k * out + j] : 0.f;
       }
   }
-  for (int i = i0 + tid; i < i1; i += NT) {
-    sm[P.am + i - i0] = gm[i];
-    sm[P.av + i - i0] = gv[i];
+  for (int i = tid; i < P.chunk; i += NT) {
+    sm[P.am + i] = i0 + i < i1 ? gm[i0 + i] : 0.f;
+    sm[P.av + i] = i0 + i < i1 ? gv[i0 + i] : 0.f;
+  }
+  int *tab = reinterpret_cast<int *>(sm + P.tab);
+  for (int i = tid; i < FIT_CLUSTER * P.chunk; i += NT) {
+    sm[P.dwp + i] = 0.f;
+    int code = 0xffff;  // padding: no such parameter
+    if (i < d.n_params) {
+      int off_w, off_wt;
+      float l2;
+      locate(i, off_w, off_wt, l2);
+      code = off_w | (off_wt + 1) << 16;
+    }
+    tab[i] = code;
   }
   if (tid < 4) sm[P.slots + tid] = 0.f;
   long long t_step = a.adam_t[model];
-  cluster_sync_all();  // everybody's shared memory exists and is initialised
+  uint32_t peer[FIT_CLUSTER];  // base of every CTA's dynamic shared memory
+#pragma unroll
+  for (int c = 0; c < FIT_CLUSTER; ++c) peer[c] = dsmem_addr(sm, c);
+  gather(0, 0);
+  cluster_arrive();
+  cluster_wait();  // everybody's shared memory exists and is initialised
 
-  const int steps_per_epoch = (a.N + a.batch - 1) / a.batch;
   int par = 0;  // slot parity of the current step
   for (int ep = 0; ep < a.epochs; ++ep) {
     float epoch_tot = 0.f;
@@ -548,29 +638,15 @@ fit_cluster_kernel(const FitCArgs a) {
       const int s0 = st * a.batch;
       const int nb = min(a.batch, a.N - s0);
       const int spc = (nb + FIT_CLUSTER - 1) / FIT_CLUSTER;  // samples per CTA
-      const int p0 = rank * spc;
-      const int mine = max(0, min(spc, nb - p0));             // this CTA's samples
-      // ---- gather this CTA's slice of the minibatch (transposed, zero padded) ----
-      for (int p = tid; p < SP; p += NT) {
-        const int row = p < mine ? perm[(size_t)ep * a.N + s0 + p0 + p] : -1;
-        idxb[p] = row;
-        sm[P.zb + p] = row >= 0 ? zg[row] : 0.f;
-      }
-      __syncthreads();
-      for (int e = tid; e < SP * D; e += NT) {
-        const int p = e / D, k = e - p * D;
-        const int row = idxb[p];
-        sm[P.h[0] + k * SP + p] = row >= 0 ? X[(size_t)row * D + k] : 0.f;
-      }
-      __syncthreads();
+      const int mine = max(0, min(spc, nb - rank * spc));     // this CTA's samples
 
-      // ---- forward ----
+      // ---- forward (the minibatch slice is already in place) ----
       for (int l = 0; l < L; ++l) {
-        const int in = d.dims[l], out = d.dims[l + 1], JP = r4(out);
+        const int in = d.dims[l], out = d.dims[l + 1];
         const float *bs = sm + P.b[l];
         float *H = sm + P.h[l + 1];
         const int act = (l == L - 1) ? BORE_ACT_LINEAR : d.act[l];  // loss works on the logit
-        dense_pass(sm + P.h[l], sm + P.w[l], in, JP, out, SP, [&](int j, int q, float4 acc) {
+        dense_pass(sm + P.h[l], sm + P.w[l], in, ldo(out), out, SP, [&](int j, int q, float4 acc) {
           const float b = bs[j];
           float4 o;
           o.x = f_act(act, acc.x + b);
@@ -610,13 +686,13 @@ fit_cluster_kernel(const FitCArgs a) {
       // ---- reverse: per layer, delta_{l-1} and this CTA's partial dW_l / db_l ----
       int cur = 0;
       for (int l = L - 1; l >= 0; --l) {
-        const int in = d.dims[l], out = d.dims[l + 1], KP = r4(in);
+        const int in = d.dims[l], out = d.dims[l + 1];
         const float *DL = sm + P.dl[cur];  // delta_l [out][SP]
         const float *Hin = sm + P.h[l];
         if (l > 0) {
           float *DN = sm + P.dl[cur ^ 1];
           const int actp = d.act[l - 1];
-          dense_pass(DL, sm + P.wt[l], out, KP, in, SP, [&](int k, int q, float4 acc) {
+          dense_pass(DL, sm + P.wt[l], out, ldo(in), in, SP, [&](int k, int q, float4 acc) {
             const float4 hv = *reinterpret_cast<const float4 *>(Hin + k * SP + 4 * q);
             float4 o;
             o.x = acc.x * f_act_bwd(actp, hv.x);
@@ -678,69 +754,91 @@ fit_cluster_kernel(const FitCArgs a) {
         cur ^= 1;
       }
 
-      cluster_sync_all();  // every CTA's partial gradient is complete
+      cluster_arrive();
+      cluster_wait();  // every CTA's partial gradient is complete
 
-      // ---- reduce slice `rank` over the cluster, Adam, scatter the new weights to every CTA ----
+      // ---- reduce slice `rank` over the cluster (4 parameters per thread), Adam in place ----
       float reg = 0.f;
-      for (int i = i0 + tid; i < i1; i += NT) {
-        float g = 0.f;
-#pragma unroll
-        for (int c = 0; c < FIT_CLUSTER; ++c) g += dsmem_ld(dsmem_addr(sm + P.dwp + i, c));
-        // which parameter is flat index i?
-        int l = 0;
-        while (l + 1 < L && i >= d.w_off[l + 1]) ++l;
-        const int in = d.dims[l], out = d.dims[l + 1];
-        const bool is_bias = i >= d.b_off[l];
-        int off_w, off_wt = -1;
-        float l2;
-        if (is_bias) {
-          off_w = P.b[l] + (i - d.b_off[l]);
-          l2 = a.l2b[l];
-        } else {
-          const int e = i - d.w_off[l], k = e / out, j = e - k * out;
-          off_w = P.w[l] + k * r4(out) + j;
-          if (l > 0) off_wt = P.wt[l] + j * r4(in) + k;
-          l2 = a.l2k[l];
-        }
-        float wv = sm[off_w];
-        if (l2 != 0.f) { reg += l2 * wv * wv; g += 2.f * l2 * wv; }
-        float m = sm[P.am + i - i0], v = sm[P.av + i - i0];
-        m += (g - m) * om1;
-        v += (g * g - v) * om2;
-        wv -= (m * alpha) / (sqrtf(v) + a.eps);
-        sm[P.am + i - i0] = m;
-        sm[P.av + i - i0] = v;
+      for (int i4 = 4 * tid; i4 < P.chunk; i4 += 4 * NT) {
+        float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < FIT_CLUSTER; ++c) {
-          dsmem_st(dsmem_addr(sm + off_w, c), wv);
-          if (off_wt >= 0) dsmem_st(dsmem_addr(sm + off_wt, c), wv);
+          const float4 t = dsmem_ld4(peer[c] + (uint32_t)(P.dwp + i0 + i4) * 4u);
+          g4.x += t.x; g4.y += t.y; g4.z += t.z; g4.w += t.w;
         }
+        float gs[4] = {g4.x, g4.y, g4.z, g4.w};
+        float outv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = i0 + i4 + e;
+          outv[e] = 0.f;
+          if (i < i1) {
+            int off_w, off_wt;
+            float l2;
+            locate(i, off_w, off_wt, l2);
+            float wv = sm[off_w], g = gs[e];
+            if (l2 != 0.f) { reg += l2 * wv * wv; g += 2.f * l2 * wv; }
+            float m = sm[P.am + i4 + e], v = sm[P.av + i4 + e];
+            m += (g - m) * om1;
+            v += (g * g - v) * om2;
+            wv -= (m * alpha) / (sqrtf(v) + a.eps);
+            sm[P.am + i4 + e] = m;
+            sm[P.av + i4 + e] = v;
+            outv[e] = wv;
+          }
+        }
+        // published to the peers after the next barrier; rewritten only after the barrier that
+        // follows their next backward pass, i.e. after they have all pulled it
+        *reinterpret_cast<float4 *>(sm + P.wn + i4) = make_float4(outv[0], outv[1], outv[2], outv[3]);
       }
       if (a.any_l2) {
         reg = block_sum(reg, red);
         if (tid == 0) sm[P.slots + 2 + par] = reg;
       }
 
-      cluster_sync_all();  // new weights everywhere; loss / reg slots of this step published
+      cluster_arrive();
+      // the next minibatch does not depend on the weights: gather it while the barrier completes
+      {
+        int nst = st + 1, nep = ep;
+        if (nst == steps_per_epoch) { nst = 0; ++nep; }
+        if (nep < a.epochs) gather(nep, nst);
+      }
+      cluster_wait();  // updated slices (and this step's loss / reg slots) are published
 
+      // ---- pull every slice from its owner, rewrite the local W / W^T / bias images ----
+      for (int i4 = 4 * tid; i4 < FIT_CLUSTER * P.chunk; i4 += 4 * NT) {
+        const int c = i4 / P.chunk, r = i4 - c * P.chunk;
+        const float4 t = dsmem_ld4(peer[c] + (uint32_t)(P.wn + r) * 4u);
+        const int4 cd = *reinterpret_cast<const int4 *>(tab + i4);
+        const float vs[4] = {t.x, t.y, t.z, t.w};
+        const int cs[4] = {cd.x, cd.y, cd.z, cd.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int off_w = cs[e] & 0xffff, off_wt = (cs[e] >> 16) - 1;
+          if (off_w != 0xffff) {
+            sm[off_w] = vs[e];
+            if (off_wt >= 0) sm[off_wt] = vs[e];
+          }
+        }
+      }
       if (rank == 0 && tid == 0) {
         float ls = 0.f, rg = 0.f;
         for (int c = 0; c < FIT_CLUSTER; ++c) {
-          ls += dsmem_ld(dsmem_addr(sm + P.slots + par, c));
-          if (a.any_l2) rg += dsmem_ld(dsmem_addr(sm + P.slots + 2 + par, c));
+          ls += dsmem_ld(peer[c] + (uint32_t)(P.slots + par) * 4u);
+          if (a.any_l2) rg += dsmem_ld(peer[c] + (uint32_t)(P.slots + 2 + par) * 4u);
         }
         epoch_tot += (ls * inv_nb + rg) * (float)nb;
       }
+      __syncthreads();  // images rewritten before the next forward
     }
     if (rank == 0 && tid == 0 && a.loss_out)
       a.loss_out[(size_t)cl * a.epochs + ep] = epoch_tot / (float)a.N;
   }
 
   // ---- write back: rank 0 the weights, every CTA its Adam slice ----
-  __syncthreads();
   if (rank == 0) {
     for (int l = 0; l < L; ++l) {
-      const int in = d.dims[l], out = d.dims[l + 1], JP = r4(out);
+      const int in = d.dims[l], out = d.dims[l + 1], JP = ldo(out);
       for (int e = tid; e < in * out; e += NT) {
         const int k = e / out, j = e - k * out;
         gp[d.w_off[l] + e] = sm[P.w[l] + k * JP + j];
@@ -753,7 +851,8 @@ fit_cluster_kernel(const FitCArgs a) {
     gm[i] = sm[P.am + i - i0];
     gv[i] = sm[P.av + i - i0];
   }
-  cluster_sync_all();  // nobody exits while a peer may still read its shared memory
+  cluster_arrive();
+  cluster_wait();  // nobody exits while a peer may still read its shared memory
 }
 
 // ---------------------------------------------------------------- evaluate (loss, accuracy)
@@ -827,7 +926,7 @@ int bore_mlp_fit(bore_mlp *h, int model0, int count, const float *X_dev, const f
     FitCPlan CP;
     make_fitc_plan(a.d, B, CP);
     const size_t csmem = (size_t)CP.total * sizeof(float);
-    const bool fits = csmem <= 200 * 1024;
+    const bool fits = csmem <= 226 * 1024 && CP.wend < 0xffff;
     const bool want = h->fit_mode == 2 || (h->fit_mode == 0 && count * FIT_CLUSTER <= h->sm_count);
     BORE_CHECK(!(h->fit_mode == 2 && !fits), "bore_mlp_fit: cluster mode needs %zu B of shared memory", csmem);
     if (want && fits) {
@@ -841,7 +940,7 @@ int bore_mlp_fit(bore_mlp *h, int model0, int count, const float *X_dev, const f
       c.lr = a.lr; c.beta1 = a.beta1; c.beta2 = a.beta2; c.eps = a.eps;
       BORE_CUDA(cudaFuncSetAttribute(fit_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)csmem));
-      fit_cluster_kernel<<<count * FIT_CLUSTER, FIT_THREADS, csmem, (cudaStream_t)stream>>>(c);
+      fit_cluster_kernel<<<count * FIT_CLUSTER, FIT_CTHREADS, csmem, (cudaStream_t)stream>>>(c);
       BORE_CUDA(cudaGetLastError());
       return 0;
     }
