@@ -50,7 +50,7 @@ static_assert(sizeof(LbScal) <= SCAL_BYTES, "LbScal grew past its slot");
 
 struct LbLayout {
   // offsets in bytes from the workspace base
-  size_t lo, hi, nbd, cnt, evals, lists, xf, f, g, pend, blocks, block_stride, total;
+  size_t lo, hi, nbd, cnt, work, evals, lists, xf, f, g, pend, blocks, block_stride, total;
 };
 
 __host__ __device__ inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
@@ -62,6 +62,7 @@ inline LbLayout make_layout(int S, int n, int m) {
   L.hi = o; o += align_up(n * sizeof(double), 16);
   L.nbd = o; o += align_up(n * sizeof(int), 16);
   L.cnt = o; o += 16;      // 3 rotating active counters (+pad)
+  L.work = o; o += 16;     // 3 rotating work-queue heads (+pad)
   L.evals = o; o += 16;    // unsigned long long evals, bytes
   L.lists = o; o += align_up((size_t)2 * S * sizeof(int), 16);
   L.xf = o; o += align_up((size_t)S * n * sizeof(float), 16);
@@ -86,6 +87,7 @@ struct LbDev {
   const void *G;  // [S][n] gradients
   int *lists;     // [2][S]
   int *cnt;       // [3]
+  int *work;      // [3] work-queue heads: next unclaimed position of the round's active list
   unsigned long long *evals;
   unsigned long long *bytes;  // algorithmic bytes moved by the stepper
   int *pend;      // [S] (may be NULL)
@@ -118,6 +120,7 @@ __global__ void __launch_bounds__(128) lbfgsb_init_kernel(LbDev D, const double 
   const int lane = threadIdx.x & 31;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     D.cnt[0] = D.S; D.cnt[1] = 0; D.cnt[2] = 0;
+    D.work[0] = 0; D.work[1] = 0; D.work[2] = 0;
     *D.evals = 0ULL;
     *D.bytes = 0ULL;
   }
@@ -200,13 +203,22 @@ __device__ __forceinline__ void fence_async_smem() {  // generic-proxy smem writ
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// the limited-memory matrices arrive with the rest of the block; only the bookkeeping of what
-// has to be written back is left
+// Barriers per new iteration at which the warps of a CTA re-align (lb_advance's mem.phase()).
+constexpr int LB_NPHASE = 4;
+
+// the limited-memory matrices arrive with the rest of the block; what is left is the
+// bookkeeping of what has to be written back, and the phase barriers
 struct BlockMem {
   bool loaded = false, is_dirty = false, vec_dirty = false;
+  int nph = 0;
   __device__ void load() { loaded = true; }
   __device__ void dirty() { is_dirty = true; }
   __device__ void dirty_vec() { vec_dirty = true; }
+  // every warp of the CTA passes exactly LB_NPHASE of these per heavy pass (the kernel pads);
+  // retries beyond that run unaligned
+  __device__ void phase() {
+    if (nph < LB_NPHASE) { __syncthreads(); ++nph; }
+  }
 };
 
 // CTA header in dynamic shared memory: formk output map | lo | hi | nbd | one mbarrier per warp
@@ -215,6 +227,13 @@ __host__ __device__ inline size_t lb_header_bytes(int n, int wpb) {
          align_up(n * sizeof(int), 16) + align_up(wpb * sizeof(uint64_t), 16);
 }
 
+// One round.  Work items (positions of the round's active list) are claimed dynamically from a
+// global queue head.  A warp runs the LIGHT stage of consecutive items (consume f,g, line-search
+// logic, termination tests: small code, most often ending in the next trial point) until it
+// holds an item that needs a new iteration; then all warps of the CTA meet and run the HEAVY
+// stage (memory update, Cauchy point, K factorisation, subspace minimisation) phase by phase
+// between CTA barriers -- ~10^4 instructions that the warps now fetch together instead of each
+// thrashing the instruction caches from a different place (profiles/r01_notes.md).
 template <typename FG>
 __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t warp_bytes) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -222,11 +241,12 @@ __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t w
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int cur = round % 3, nxt = (round + 1) % 3, clr = (round + 2) % 3;
-  if (blockIdx.x == 0 && threadIdx.x == 0) D.cnt[clr] = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { D.cnt[clr] = 0; D.work[clr] = 0; }
   const int n_active = D.cnt[cur];
   if (blockIdx.x * wpb >= n_active) return;
   const int *list_cur = D.lists + (size_t)(round & 1) * D.S;
   int *list_nxt = D.lists + (size_t)((round + 1) & 1) * D.S;
+  int *qhead = D.work + cur;
 
   // ---- CTA header ----
   int *ftab = reinterpret_cast<int *>(smem_raw);
@@ -238,18 +258,25 @@ __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t w
   uint64_t *bar = bars + wib;
   unsigned char *base = smem_raw + lb_header_bytes(n, wpb) + warp_bytes * wib;
   const uint32_t block_bytes = (uint32_t)(LB_PERSIST_DOUBLES(n, m) * sizeof(double));
-  const int stride = gridDim.x * wpb;
-  int idx = blockIdx.x * wpb + wib;
 
-  // the first start's block is on its way while the header is being filled
+  // claim a position of the active list (>= n_active: the list is exhausted)
+  auto claim = [&]() {
+    int v = 0;
+    if (lane == 0) v = atomicAdd(qhead, 1);
+    return __shfl_sync(0xffffffffu, v, 0);
+  };
+  // cur_i: the item whose block is staged (or on its way) in this warp's workspace;
+  // nxt_i: the one after it, already claimed and prefetched into L2
+  int cur_i = claim();
   if (lane == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (idx < n_active) {
+    if (cur_i < n_active) {
       mbar_expect_tx(bar, block_bytes);
-      bulk_g2s(base, D.blocks + D.block_stride * list_cur[idx], block_bytes, bar);
+      bulk_g2s(base, D.blocks + D.block_stride * list_cur[cur_i], block_bytes, bar);
     }
   }
+  int nxt_i = n_active;
 #pragma unroll 1
   for (int o = threadIdx.x; o < LB_FORMK_ACC * 32; o += blockDim.x) ftab[o] = lbw::lb_formk_code(o, m);
 #pragma unroll 1
@@ -270,38 +297,19 @@ __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t w
   const FG *F = static_cast<const FG *>(D.F);
   const FG *G = static_cast<const FG *>(D.G);
   uint32_t parity = 0;
+  unsigned long long my_bytes = 0, my_evals = 0;
 
-#pragma unroll 1
-  for (; idx < n_active; idx += stride) {
-    const int sid = list_cur[idx];
+  LbScal s;
+  BlockMem mem;
+  int sid = 0, col_in = 0;
+  bool was_ls = false;
+
+  // write an item back and put the next one on its way
+  auto finish = [&](int pend) {
     char *gblock = D.blocks + D.block_stride * sid;
     double *xr = D.xreq + (size_t)sid * n;
-    const FG *gr = G + (size_t)sid * n;
-    // pull the block of this warp's next start into L2 while this one is being worked on
-    if (lane == 0 && idx + stride < n_active)
-      bulk_prefetch_l2(D.blocks + D.block_stride * list_cur[idx + stride], block_bytes);
-
-    const double fval = (double)F[sid];
-#pragma unroll 1
-    for (int i = lane; i < n; i += 32) {
-      w.x[i] = xr[i];
-      w.g[i] = (double)gr[i];
-      const int nb = s_nbd[i];
-      w.iwhere[i] = nb == 0 ? -1 : ((nb == 2 && s_hi[i] - s_lo[i] <= 0.0) ? 3 : 0);
-    }
-    mbar_wait(bar, parity);
-    parity ^= 1;
     __syncwarp();
-    LbScal s = *s_smem;
-    s.f = fval;
-    BlockMem mem;
-    const int col_in = s.col;
-    const bool was_ls = s.phase == LB_PH_LNSRCH;
-    const int pend = lbw::lb_advance(P, w, s, mem);
-    __syncwarp();
-    if (lane == 0)
-      atomicAdd(D.bytes, step_bytes(n, (int)sizeof(FG), was_ls, mem.loaded, col_in, s.col,
-                                    pend != 0, mem.is_dirty));
+    my_bytes += step_bytes(n, (int)sizeof(FG), was_ls, mem.loaded, col_in, s.col, pend != 0, mem.is_dirty);
     if (pend) {
       int changed = 0;
       float *xf = D.xf ? D.xf + (size_t)sid * n : nullptr;
@@ -317,10 +325,11 @@ __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t w
 #pragma unroll 1
       for (int i = lane; i < n; i += 32) xr[i] = w.x[i];  // final iterate
     }
-    // write back the head of the block that changed: scalars | t r d z | W and the matrices
+    // the head of the block that changed: scalars | t r d z | W and the matrices
     if (lane == 0) *s_smem = s;
     fence_async_smem();
     __syncwarp();
+    cur_i = nxt_i;
     if (lane == 0) {
       uint32_t bytes = SCAL_BYTES;
       if (pend && mem.vec_dirty) bytes += 4 * LB_NV(n) * sizeof(double);
@@ -330,19 +339,69 @@ __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t w
       if (pend) {
         const int pos = atomicAdd(&D.cnt[nxt], 1);
         list_nxt[pos] = sid;
-        atomicAdd(D.evals, 1ULL);
+        my_evals += 1;
       }
       if (D.pend) D.pend[sid] = pend;
       // the workspace may be overwritten once the store has read it
       bulk_wait_read();
-      if (idx + stride < n_active) {
+      if (cur_i < n_active) {
         mbar_expect_tx(bar, block_bytes);
-        bulk_g2s(base, D.blocks + D.block_stride * list_cur[idx + stride], block_bytes, bar);
+        bulk_g2s(base, D.blocks + D.block_stride * list_cur[cur_i], block_bytes, bar);
       }
     }
     __syncwarp();
+  };
+
+#pragma unroll 1
+  for (;;) {
+    // ---- light stages until this warp holds an item that needs a new iteration ----
+    bool holding = false;
+#pragma unroll 1
+    while (cur_i < n_active) {
+      sid = list_cur[cur_i];
+      // claim the item after this one and pull its block into L2 meanwhile
+      nxt_i = claim();
+      if (lane == 0 && nxt_i < n_active)
+        bulk_prefetch_l2(D.blocks + D.block_stride * list_cur[nxt_i], block_bytes);
+      const double *xr = D.xreq + (size_t)sid * n;
+      const FG *gr = G + (size_t)sid * n;
+      const double fval = (double)F[sid];
+#pragma unroll 1
+      for (int i = lane; i < n; i += 32) {
+        w.x[i] = xr[i];
+        w.g[i] = (double)gr[i];
+        const int nb = s_nbd[i];
+        w.iwhere[i] = nb == 0 ? -1 : ((nb == 2 && s_hi[i] - s_lo[i] <= 0.0) ? 3 : 0);
+      }
+      mbar_wait(bar, parity);
+      parity ^= 1;
+      __syncwarp();
+      s = *s_smem;
+      s.f = fval;
+      mem = BlockMem();
+      col_in = s.col;
+      was_ls = s.phase == LB_PH_LNSRCH;
+      const int r = lbw::lb_advance(P, w, s, mem, 1);
+      if (r == 2) { holding = true; break; }
+      finish(r);
+    }
+    if (!__syncthreads_or(holding ? 1 : 0)) break;
+    // ---- heavy stage, phase-aligned across the CTA ----
+    if (holding) {
+      const int r = lbw::lb_advance(P, w, s, mem, 2);
+#pragma unroll 1
+      while (mem.nph < LB_NPHASE) { __syncthreads(); ++mem.nph; }
+      finish(r);
+    } else {
+#pragma unroll 1
+      for (int k = 0; k < LB_NPHASE; ++k) __syncthreads();
+    }
   }
-  if (lane == 0) bulk_wait_all();
+  if (lane == 0) {
+    atomicAdd(D.bytes, my_bytes);
+    atomicAdd(D.evals, my_evals);
+    bulk_wait_all();
+  }
 }
 
 __global__ void lbfgsb_results_kernel(LbDev D, double *x, double *fun, int *nit, int *nfev,
@@ -441,6 +500,7 @@ int setup_params(LbDev &D, const LbLayout &L, char *work, int S, int n, int m, c
   D.block_stride = L.block_stride;
   D.lists = reinterpret_cast<int *>(work + L.lists);
   D.cnt = reinterpret_cast<int *>(work + L.cnt);
+  D.work = reinterpret_cast<int *>(work + L.work);
   D.evals = reinterpret_cast<unsigned long long *>(work + L.evals);
   D.bytes = D.evals + 1;
   return 0;

@@ -1099,11 +1099,15 @@ LB_FN void lb_matupd(const LbParams &P, LbWork &w, LbScal &s, double rr, double 
 
 // `Mem` supplies the limited-memory matrices lazily: mem.load() is called once, right before
 // they are first needed (a step that only continues a line search never touches them), and
-// mem.dirty() when they were modified.
+// mem.dirty() when they were modified.  mem.phase() marks the boundaries between the big
+// pieces of a new iteration (memory update | Cauchy point | K factorisation | subspace
+// minimisation | line-search set-up): the device kernel re-aligns the warps of a CTA there so
+// that they fetch the same instructions at the same time.
 struct LbNoMem {
   LB_FN void load() {}
   LB_FN void dirty() {}
   LB_FN void dirty_vec() {}
+  LB_FN void phase() {}
 };
 
 //
@@ -1190,6 +1194,7 @@ LB_FN int lb_advance(const LbParams &P, LbWork &w, LbScal &s, Mem &mem, int stag
       int nfree = n;
       LB_UNROLL1
       for (;;) {
+        mem.phase();  // (memory update done) -> Cauchy point
         if (!P.cnstnd && s.col > 0) {
           LB_SYNC();
           LB_FOR(i, n) { w.z[i] = w.x[i]; w.iwhere[i] = -1; }
@@ -1201,13 +1206,16 @@ LB_FN int lb_advance(const LbParams &P, LbWork &w, LbScal &s, Mem &mem, int stag
           nfree = lb_freev(P, w);
         }
         if (nfree != 0 && s.col != 0) {
+          mem.phase();  // -> K factorisation
           if (lb_formk(P, w, s, nfree)) { lb_reset_memory(s); continue; }
+          mem.phase();  // -> subspace minimisation
           int info = lb_cmprlb(P, w, s, nfree);
           if (!info) info = lb_subsm(P, w, s, nfree);
           if (info) { lb_reset_memory(s); continue; }
         }
         break;
       }
+      mem.phase();  // -> line-search set-up
       LB_SYNC();
       // ---- d = z - x and line-search set-up (lnsrlb, first part) ----
       double dtd = 0.0;
