@@ -30,6 +30,7 @@
 // 4.7 ms for 65,536 starts with the warp kernel.  profiles/r01_notes.md has the launch list.
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -203,21 +204,26 @@ __device__ __forceinline__ void fence_async_smem() {  // generic-proxy smem writ
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// Barriers per new iteration at which the warps of a CTA re-align (lb_advance's mem.phase()).
-constexpr int LB_NPHASE = 4;
+// Extra barriers per new iteration at which the warps of a CTA re-align (lb_advance's
+// mem.phase()): at most 4 (before the Cauchy point, the K factorisation, the subspace
+// minimisation and the line-search set-up).  Measured on B200, cfg 3 (stepper ms per step):
+// free-running warps 148.7, rendezvous only 124.3, +1 barrier 124.5, +2 129.6, +3 131.4,
+// +4 133.2 -- the default is the rendezvous alone (0); BORE_LB_NPHASE in the environment
+// overrides it (-1 = free-running).
+constexpr int LB_NPHASE_MAX = 4;
 
 // the limited-memory matrices arrive with the rest of the block; what is left is the
 // bookkeeping of what has to be written back, and the phase barriers
 struct BlockMem {
   bool loaded = false, is_dirty = false, vec_dirty = false;
-  int nph = 0;
+  int nph = 0, cap = LB_NPHASE_MAX;
   __device__ void load() { loaded = true; }
   __device__ void dirty() { is_dirty = true; }
   __device__ void dirty_vec() { vec_dirty = true; }
-  // every warp of the CTA passes exactly LB_NPHASE of these per heavy pass (the kernel pads);
+  // every warp of the CTA passes exactly `cap` of these per heavy pass (the kernel pads);
   // retries beyond that run unaligned
   __device__ void phase() {
-    if (nph < LB_NPHASE) { __syncthreads(); ++nph; }
+    if (nph < cap) { __syncthreads(); ++nph; }
   }
 };
 
@@ -235,7 +241,7 @@ __host__ __device__ inline size_t lb_header_bytes(int n, int wpb) {
 // between CTA barriers -- ~10^4 instructions that the warps now fetch together instead of each
 // thrashing the instruction caches from a different place (profiles/r01_notes.md).
 template <typename FG>
-__global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t warp_bytes) {
+__global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t warp_bytes, int nphase) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int n = D.P.n, m = D.P.m;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -379,22 +385,29 @@ __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t w
       s = *s_smem;
       s.f = fval;
       mem = BlockMem();
+      mem.cap = nphase < 0 ? 0 : nphase;
       col_in = s.col;
       was_ls = s.phase == LB_PH_LNSRCH;
       const int r = lbw::lb_advance(P, w, s, mem, 1);
       if (r == 2) { holding = true; break; }
       finish(r);
     }
+    if (nphase < 0) {  // free-running warps (no alignment at all): tuning / comparison mode
+      if (!holding) break;
+      const int r = lbw::lb_advance(P, w, s, mem, 2);
+      finish(r);
+      continue;
+    }
     if (!__syncthreads_or(holding ? 1 : 0)) break;
     // ---- heavy stage, phase-aligned across the CTA ----
     if (holding) {
       const int r = lbw::lb_advance(P, w, s, mem, 2);
 #pragma unroll 1
-      while (mem.nph < LB_NPHASE) { __syncthreads(); ++mem.nph; }
+      while (mem.nph < nphase) { __syncthreads(); ++mem.nph; }
       finish(r);
     } else {
 #pragma unroll 1
-      for (int k = 0; k < LB_NPHASE; ++k) __syncthreads();
+      for (int k = 0; k < nphase; ++k) __syncthreads();
     }
   }
   if (lane == 0) {
@@ -516,7 +529,14 @@ int launch_round(const LbDev &D, const StepLaunch &SL, int round, cudaStream_t s
                                    227 * 1024));
     attr_done[which] = true;
   }
-  lbfgsb_warp_kernel<FG><<<SL.grid, SL.block, SL.smem, stream>>>(D, round, SL.warp_bytes);
+  static int nphase = -1;
+  if (nphase < 0) {
+    const char *e = getenv("BORE_LB_NPHASE");
+    nphase = e ? atoi(e) : 0;
+    if (nphase < -1) nphase = -1;
+    if (nphase > LB_NPHASE_MAX) nphase = LB_NPHASE_MAX;
+  }
+  lbfgsb_warp_kernel<FG><<<SL.grid, SL.block, SL.smem, stream>>>(D, round, SL.warp_bytes, nphase);
   return 0;
 }
 
