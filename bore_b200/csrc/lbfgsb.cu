@@ -471,6 +471,14 @@ int plan_step(int S, int n, int m, int sm_count, StepLaunch &L) {
     if (ctas * c > 12) ctas = 12 / c;
     if (ctas * c >= best) { best = ctas * c; wpb = c; }
   }
+  {  // tuning knob: warps per CTA (= size of the group that meets at the rendezvous)
+    static int forced = -1;
+    if (forced < 0) {
+      const char *e = getenv("BORE_LB_WPB");
+      forced = e ? atoi(e) : 0;
+    }
+    if (forced >= 1 && forced <= 12 && forced * L.warp_bytes + hdr <= max_block) wpb = forced;
+  }
   L.block = wpb * 32;
   L.smem = hdr + wpb * L.warp_bytes;
   int per_sm = (int)(max_sm / (L.smem + 1024));

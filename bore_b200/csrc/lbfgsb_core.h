@@ -39,6 +39,8 @@
 #undef LB_SYNC
 #undef LB_FOR
 #undef LB_UNROLL1
+#undef LB_UNROLL_HOT
+#undef LB_UNROLL_HOT2
 #undef LB_NI
 #undef LB_SHARED
 // Code size is a first-order cost on the device: the stepper is ~10^4 mostly-serial
@@ -50,10 +52,14 @@
 // they still compile to LDS/STS.
 #if LB_VARIANT == 0
 #define LB_UNROLL1
+#define LB_UNROLL_HOT
+#define LB_UNROLL_HOT2
 #define LB_NI inline
 #define LB_SHARED(p) ((void)0)
 #else
 #define LB_UNROLL1 _Pragma("unroll 1")
+#define LB_UNROLL_HOT _Pragma("unroll 2")   // hot inner loops: loads of 2 iterations in flight
+#define LB_UNROLL_HOT2 _Pragma("unroll 2")
 #define LB_NI __device__ __noinline__
 #define LB_SHARED(p) __builtin_assume(__isShared(p))
 #endif
@@ -321,21 +327,21 @@ LB_NI void lb_bmv(const double *ld, const double *tinv, double *q, int m, int co
   LB_SYNC();
   LB_FOR(i, col) {
     double a = v[col + i];
-    LB_UNROLL1
+    LB_UNROLL_HOT
     for (int k = 0; k < i; ++k) a += ld[i * m + k] * v[k];
     q[i] = a;
   }
   LB_SYNC();
   LB_FOR(i, col) {
     double a = 0.0;
-    LB_UNROLL1
+    LB_UNROLL_HOT
     for (int j = 0; j < col; ++j) a += tinv[i * m + j] * q[j];
     p[col + i] = a;
   }
   LB_SYNC();
   LB_FOR(i, col) {
     double a = -ld[i * m + i] * v[i];
-    LB_UNROLL1
+    LB_UNROLL_HOT
     for (int k = i + 1; k < col; ++k) a += ld[k * m + i] * p[col + k];
     p[i] = a;
   }
@@ -356,7 +362,7 @@ LB_FN int lb_formt(LbWork &w, int m, int col, double theta) {
     const int j = LB_PAIR_HI(cd), i = LB_PAIR_LO(cd);  // i <= j
     if (j < col) {
       double a = theta * w.ss[i * m + j];
-      LB_UNROLL1
+      LB_UNROLL_HOT
       for (int k = 0; k < i; ++k) a += w.ld[i * m + k] * w.sy[j * m + k];
       T[i * m + j] = a;
     }
@@ -388,7 +394,7 @@ LB_FN int lb_formt(LbWork &w, int m, int col, double theta) {
     const int j = LB_PAIR_HI(cd), i = LB_PAIR_LO(cd);  // i <= j
     if (j < col) {
       double a = 0.0;
-      LB_UNROLL1
+      LB_UNROLL_HOT
       for (int k = j; k < col; ++k) a += Ri[i * m + k] * Ri[j * m + k];
       w.tinv[i * m + j] = a;
       w.tinv[j * m + i] = a;
@@ -499,7 +505,7 @@ LB_FN int lb_cauchy(const LbParams &P, LbWork &w, const LbScal &s, int &nseg_out
   for (int j = LB_LANE; j < col2; j += LB_NL) {
     const LbDP wc = w.W + (j < col ? j : m + (j - col));
     double a = 0.0;
-    LB_UNROLL1
+    LB_UNROLL_HOT
     for (int i = 0; i < n; ++i) a += wc[i * ldw] * d[i];
     w.p[j] = j < col ? a : theta * a;
     w.c[j] = 0.0;
@@ -744,7 +750,7 @@ LB_FN int lb_formk(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
     acc[t] = 0.0;
     code[t] = w.ftab[LB_LANE + 32 * t];
   }
-  LB_UNROLL1
+  LB_UNROLL_HOT2
   for (int k = 0; k < nq; ++k) {
     const LbDP row = W + ind[k] * ldw;
 #pragma unroll
@@ -837,7 +843,7 @@ LB_FN int lb_formk(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
     const int js = LB_PAIR_HI(cd), is = LB_PAIR_LO(cd);  // is <= js
     if (js < col) {
       double a = 0.0;
-      LB_UNROLL1
+      LB_UNROLL_HOT
       for (int k = 0; k < col; ++k) a += w.wn[k * ldn + col + is] * w.wn[k * ldn + col + js];
       w.wn[(col + is) * ldn + col + js] += a;
     }
@@ -879,7 +885,7 @@ LB_FN int lb_cmprlb(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
     if (w.iwhere[i] <= 0) {
       double a = -theta * (w.z[i] - w.x[i]) - w.g[i];
       const LbDP row = w.W + i * ldw;
-      LB_UNROLL1
+      LB_UNROLL_HOT
       for (int j = 0; j < col; ++j) a += row[j] * w.p[j] + row[m + j] * (theta * w.p[col + j]);
       w.r[i] = a;
     } else {
@@ -905,7 +911,7 @@ LB_FN int lb_subsm(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
   for (int j = LB_LANE; j < col2; j += LB_NL) {
     const LbDP wc = w.W + (j < col ? j : m + (j - col));
     double a = 0.0;
-    LB_UNROLL1
+    LB_UNROLL_HOT
     for (int k = 0; k < nfree; ++k) { const int i = w.index[k]; a += wc[i * ldw] * w.r[i]; }
     wv[j] = j < col ? a : theta * a;
   }
@@ -944,7 +950,7 @@ LB_FN int lb_subsm(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
     if (w.iwhere[i] <= 0) {
       double dk = w.r[i];
       const LbDP row = w.W + i * ldw;
-      LB_UNROLL1
+      LB_UNROLL_HOT
       for (int j = 0; j < col; ++j) dk += row[j] * wv[j] + row[m + j] * wv[col + j];
       dk *= 1.0 / theta;
       w.r[i] = dk;
@@ -1030,7 +1036,7 @@ LB_FN void lb_matupd(const LbParams &P, LbWork &w, LbScal &s, double rr, double 
   } else {
     LB_FOR(i, n) {
       LbDP row = w.W + i * ldw;
-      LB_UNROLL1
+      LB_UNROLL_HOT
       for (int j = 0; j < m - 1; ++j) { row[j] = row[j + 1]; row[m + j] = row[m + j + 1]; }
     }
     // new(i,j) = old(i+1,j+1) for the three (m-1) x (m-1) leading blocks of sy, ss, yy
@@ -1073,7 +1079,7 @@ LB_FN void lb_matupd(const LbParams &P, LbWork &w, LbScal &s, double rr, double 
     const int j = is_y ? jl : jl - last;
     const LbDP colp = w.W + (is_y ? j : m + j);
     double a_s = 0.0, a_y = 0.0;
-    LB_UNROLL1
+    LB_UNROLL_HOT
     for (int i = 0; i < n; ++i) {
       const double c = colp[i * ldw];
       a_s += w.d[i] * c;
