@@ -17,6 +17,8 @@
 //            both weight layouts rewritten; Adam slots m, v stream through L2.
 // Weights never leave shared memory during the run; HBM traffic is the minibatch gather
 // (B*(D+1)*4 bytes per step) plus the per-epoch loss.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -946,7 +948,21 @@ int bore_mlp_fit(bore_mlp *h, int model0, int count, const float *X_dev, const f
     }
   }
   BORE_CUDA(cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fit_kernel<<<count, FIT_THREADS, smem, (cudaStream_t)stream>>>(a);
+  // threads per CTA: a step is a chain of ~16 barrier-separated phases whose length hardly depends
+  // on the thread count for small nets, so with more models than CTA slots the throughput is set
+  // by how many CTAs are resident -- smaller CTAs, more of them (BORE_FIT_THREADS overrides)
+  // measured, cfg 4 (4,096 x Dense32x2 models, ms per BO iteration of all of them):
+  // 256 threads 462, 128 threads 314, 64 threads 332, 32 threads 397
+  int threads = count >= 2 * h->sm_count ? 128 : FIT_THREADS;
+  {
+    static int forced = -1;
+    if (forced < 0) {
+      const char *e = getenv("BORE_FIT_THREADS");
+      forced = e ? atoi(e) : 0;
+    }
+    if (forced == 32 || forced == 64 || forced == 128 || forced == 256) threads = forced;
+  }
+  fit_kernel<<<count, threads, smem, (cudaStream_t)stream>>>(a);
   BORE_CUDA(cudaGetLastError());
   return 0;
 }
