@@ -61,7 +61,10 @@ SIGNATURES = {
                                              C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
                                              vp, C.c_size_t, vp, vp, vp, vp, vp, vp,
                                              c_int_p, C.POINTER(C.c_longlong), vp]),
-    "bore_select_best_groups": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, C.c_int, vp]),
+    "bore_select_best_groups": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, C.c_int, vp]),
+    "bore_quantile_labels": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, vp, vp, vp, C.c_int, vp]),
+    "bore_is_duplicate": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_double, C.c_double,
+                                    vp, vp, C.c_int, vp]),
     "bore_bench_ffma_peak": (C.c_int, [C.c_int, C.c_int, c_double_p]),
 }
 

@@ -81,9 +81,12 @@ class BatchedMaximizableSequential:
     def get_weights(self):
         return [self._net.get_weights(model=p) for p in range(self.n_problems)]
 
-    def fit(self, x, y, batch_size=32, epochs=1, permutations=None, shuffle=True, verbose=0):
+    def fit(self, x, y, batch_size=32, epochs=1, permutations=None, shuffle=True, verbose=0,
+            gamma=None):
         """x (M, N, D), y (M, N): every problem trains on its own N observations, all in one
         launch.  ``permutations``: (epochs, N) shared by all problems or (M, epochs, N).
+        With ``gamma`` given, ``y`` holds the RAW targets and every problem is labelled
+        ``z = y < quantile(y, gamma)`` on the device (bore/data.py:31-35) before training.
         Returns the per-problem history loss, shape (M, epochs)."""
         if not self._compiled:
             raise RuntimeError("You must compile your model before training/testing.")
@@ -91,6 +94,10 @@ class BatchedMaximizableSequential:
         z = np.asarray(y)
         M, N, D = X.shape
         assert M == self.n_problems and z.shape == (M, N) and D == self.dims[0]
+        z_dev = None
+        if gamma is not None:
+            z_dev = self._net.quantile_labels_dev(
+                self._net.to_device(np.ascontiguousarray(z, np.float64), np.float64), gamma).reshape(-1)
         if permutations is None:
             if shuffle:
                 permutations = np.stack([np.stack([self._rs.permutation(N) for _ in range(epochs)])
@@ -102,6 +109,7 @@ class BatchedMaximizableSequential:
         assert perm.shape == ((epochs, N) if shared_perm else (M, epochs, N))
         net = self._net
         loss = net.fit_dev(net.to_device(X.reshape(M * N, D), np.float32),
+                           z_dev if z_dev is not None else
                            net.to_device(z.reshape(-1).astype(np.float32), np.float32),
                            N, int(batch_size), int(epochs), net.to_device(perm, np.int32),
                            model0=0, count=M, shared_data=False, shared_perm=shared_perm)
@@ -120,11 +128,14 @@ class BatchedMaximizableSequential:
 
     # ------------------------------------------------------------------ argmax per problem
     def argmax(self, bounds, num_starts=5, num_samples=1024, method="L-BFGS-B",
-               options=dict(maxiter=1000, ftol=1e-9), random_state=None, X_init=None):
+               options=dict(maxiter=1000, ftol=1e-9), random_state=None, X_init=None,
+               exclude=None, rtol=1e-5, atol=1e-8):
         """One ``OptimizeResult`` (or None) per problem: bore/mixins.py:22-89 for each of them.
         ``random_state`` draws the (M, num_samples, D) screening samples problem after problem
         (what M sequential ``argmax`` calls sharing one RandomState would consume); ``X_init``
-        overrides the draw."""
+        overrides the draw.  ``exclude`` (M, N, D): each problem's stored observations -- results
+        ``np.allclose`` to one of them are dropped before the selection, which is the plugin's
+        ``filter_fn=_is_unique`` (bore/plugins/hpbandster/base.py:227-231, bore/data.py:42-48)."""
         import torch
         assert num_samples >= num_starts > 0
         if method != "L-BFGS-B":
@@ -150,7 +161,13 @@ class BatchedMaximizableSequential:
                                    m=opts.get("maxcor", 10), ftol=opts.get("ftol", 2.2204460492503131e-09),
                                    gtol=opts.get("gtol", 1e-5), maxiter=opts.get("maxiter", 15000),
                                    maxfun=opts.get("maxfun", 15000), maxls=opts.get("maxls", 20))
-        keys = net.select_best_groups(res["fun"], res["status"])
+        keep = None
+        if exclude is not None:
+            prev = np.ascontiguousarray(exclude, np.float64)
+            assert prev.ndim == 3 and prev.shape[0] == M and prev.shape[2] == dim
+            if prev.shape[1] > 0:
+                keep = net.keep_unique_dev(res["x"], net.to_device(prev, np.float64), rtol=rtol, atol=atol)
+        keys = net.select_best_groups(res["fun"], res["status"], keep_dev=keep)
         self._last_stats = dict(evals=res["evals"], rounds=res["rounds"], num_starts=num_starts)
         # one small record per problem leaves the GPU
         win = (0x7fffffff - (keys & 0x7fffffff)).clamp(0, num_starts - 1)

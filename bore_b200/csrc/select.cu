@@ -133,7 +133,8 @@ topk_groups_kernel(const float *__restrict__ f, int P, int n_pow2, int k, float 
 // first minimum of every group of `per_group` results: one warp per group
 __global__ void __launch_bounds__(128)
 select_best_groups_kernel(const double *__restrict__ fun, const int32_t *__restrict__ status,
-                          int n_groups, int per_group, unsigned long long *__restrict__ keys) {
+                          const uint8_t *__restrict__ keep, int n_groups, int per_group,
+                          unsigned long long *__restrict__ keys) {
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (g >= n_groups) return;
   unsigned long long best = 0ULL;
@@ -141,6 +142,7 @@ select_best_groups_kernel(const double *__restrict__ fun, const int32_t *__restr
     const size_t q = (size_t)g * per_group + i;
     const int st = status[q];
     if (!(st == 0 || st == 1)) continue;
+    if (keep && !keep[q]) continue;
     const float v = (float)fun[q];
     if (v != v) continue;
     const unsigned long long key = ((unsigned long long)orderable(-v) << 31) |
@@ -230,14 +232,16 @@ int bore_topk_smallest_groups(const float *f_dev, int n_groups, int per_group, i
   return 0;
 }
 
-int bore_select_best_groups(const double *fun_dev, const int32_t *status_dev, int n_groups,
-                            int per_group, int64_t *keys_dev, int device, void *stream_) {
+int bore_select_best_groups(const double *fun_dev, const int32_t *status_dev,
+                            const uint8_t *keep_dev, int n_groups, int per_group, int64_t *keys_dev,
+                            int device, void *stream_) {
   BORE_CHECK(n_groups >= 1 && per_group >= 1 && fun_dev && status_dev && keys_dev,
              "bore_select_best_groups: bad arguments");
   BORE_CHECK(bore_device_count() > 0, "no CUDA device visible -- bore_b200 has no CPU fallback");
   BORE_CUDA(cudaSetDevice(device));
   select_best_groups_kernel<<<(n_groups * 32 + 127) / 128, 128, 0, (cudaStream_t)stream_>>>(
-      fun_dev, status_dev, n_groups, per_group, reinterpret_cast<unsigned long long *>(keys_dev));
+      fun_dev, status_dev, keep_dev, n_groups, per_group,
+      reinterpret_cast<unsigned long long *>(keys_dev));
   BORE_CUDA(cudaGetLastError());
   return 0;
 }

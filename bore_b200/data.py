@@ -1,4 +1,7 @@
-"""Observation store feeding ``fit`` (mirror of bore/data.py:4-48).  Host-side numpy only.
+"""Observation store feeding ``fit`` (mirror of bore/data.py:4-48), plus the device form of its
+two computations: ``quantile_labels`` (bore/data.py:31-35 for many
+problems at once) and ``UniqueFilter`` (bore/data.py:42-48 as the ``filter_fn`` of ``argmax``,
+evaluated for every result in one launch instead of one Python callback per result).
 
 ``MultiFidelityRecord`` (bore/data.py:51-261) feeds the LSTM plugin only and is out of scope
 (SURVEY.md section 8f)."""
@@ -41,3 +44,35 @@ class Record:
             if np.allclose(x_prev, x, rtol=rtol, atol=atol):
                 return True
         return False
+
+
+def quantile_labels(y, gamma, net):
+    """``z = y < np.quantile(y, gamma)`` per row of ``y`` (M, N), computed by the
+    ``bore_quantile_labels`` kernel of ``net`` (a ``NativeMLP``); returns (z bool (M, N), tau (M,)).
+    Bit-identical to bore/data.py:33-34 applied row by row."""
+    y = np.ascontiguousarray(np.atleast_2d(np.asarray(y, np.float64)))
+    z, tau = net.quantile_labels_dev(net.to_device(y, np.float64), gamma, want_tau=True)
+    return z.cpu().numpy() != 0, tau.cpu().numpy()
+
+
+class UniqueFilter:
+    """``filter_fn`` for ``argmax`` that rejects results already in ``record``
+    (bore/plugins/hpbandster/base.py:227-231).  Called as a function it is the reference's
+    host predicate; ``MaximizableMixin.argmax`` recognises the type and evaluates it for all
+    results at once on the device (``bore_is_duplicate``) -- same selection, no per-result
+    callback."""
+
+    def __init__(self, record, rtol=1e-5, atol=1e-8, logger=None):
+        self.record, self.rtol, self.atol, self.logger = record, rtol, atol, logger
+
+    def __call__(self, res):
+        dup = self.record.is_duplicate(res.x, rtol=self.rtol, atol=self.atol)
+        if dup and self.logger is not None:
+            self.logger.warning("Duplicate detected! Skipping...")
+        return not dup
+
+    def stored(self):
+        """(N, D) float64 matrix of the stored feature vectors (N may be 0)."""
+        if not self.record.features:
+            return np.zeros((0, 0), np.float64)
+        return np.ascontiguousarray(self.record.load_feature_matrix(), np.float64)

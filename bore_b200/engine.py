@@ -339,16 +339,45 @@ class NativeMLP:
         return dict(x=x, fun=fun, nit=ints[0], nfev=ints[1], status=ints[2], task=ints[3],
                     rounds=rounds.value, evals=evals.value)
 
-    def select_best_groups(self, fun_dev, status_dev):
+    def select_best_groups(self, fun_dev, status_dev, keep_dev=None):
         """(M, K) results -> int64 (M,) keys; key & 0x7fffffff = 0x7fffffff - winner's index in
-        its group, key 0 = no start of the group qualifies."""
+        its group, key 0 = no start of the group qualifies.  ``keep_dev`` (M, K) uint8: filter mask."""
         torch = _torch()
         M, K = fun_dev.shape
         assert fun_dev.dtype == torch.float64 and status_dev.dtype == torch.int32
+        assert keep_dev is None or (keep_dev.dtype == torch.uint8 and keep_dev.shape == (M, K))
         keys = torch.empty(M, dtype=torch.int64, device=self._tdev())
-        _lib.check(self.lib.bore_select_best_groups(_ptr(fun_dev), _ptr(status_dev), int(M), int(K),
-                                                    _ptr(keys), self.device, self._stream()))
+        _lib.check(self.lib.bore_select_best_groups(_ptr(fun_dev), _ptr(status_dev), _ptr(keep_dev),
+                                                    int(M), int(K), _ptr(keys), self.device,
+                                                    self._stream()))
         return keys
+
+    # ------------------------------------------------------------------ data step (section 8f row 2)
+    def quantile_labels_dev(self, y_dev, gamma, want_tau=False):
+        """y_dev (M, N) float64 -> z (M, N) float32 of 0/1 (and tau (M,)): bore/data.py:31-35 on
+        the device for M problems at once."""
+        torch = _torch()
+        assert y_dev.dtype == torch.float64 and y_dev.dim() == 2 and y_dev.is_contiguous()
+        M, N = y_dev.shape
+        z = torch.empty(M, N, dtype=torch.float32, device=self._tdev())
+        tau = torch.empty(M, dtype=torch.float64, device=self._tdev()) if want_tau else None
+        _lib.check(self.lib.bore_quantile_labels(_ptr(y_dev), int(M), int(N), float(gamma), _ptr(z), None,
+                                                 _ptr(tau), self.device, self._stream()))
+        return (z, tau) if want_tau else z
+
+    def keep_unique_dev(self, x_dev, x_prev_dev, rtol=1e-5, atol=1e-8):
+        """x_dev (G, K, D), x_prev_dev (G, N, D) float64 -> keep (G, K) uint8: 0 where the
+        candidate is np.allclose to a stored row of its group (bore/data.py:42-48)."""
+        torch = _torch()
+        G, K, D = x_dev.shape
+        assert x_dev.dtype == torch.float64 and x_dev.is_contiguous()
+        assert x_prev_dev.dtype == torch.float64 and x_prev_dev.is_contiguous()
+        assert x_prev_dev.shape[0] == G and x_prev_dev.shape[2] == D
+        keep = torch.empty(G, K, dtype=torch.uint8, device=self._tdev())
+        _lib.check(self.lib.bore_is_duplicate(_ptr(x_dev), int(G), int(K), _ptr(x_prev_dev),
+                                              int(x_prev_dev.shape[1]), int(D), float(rtol), float(atol),
+                                              None, _ptr(keep), self.device, self._stream()))
+        return keep
 
     # ------------------------------------------------------------------ K1
     def fit_dev(self, X_dev, z_dev, N, batch_size, epochs, perm_dev, loss_dev=None,

@@ -128,7 +128,9 @@ class MaximizableMixin:
         kw.update(dict(zip(names, args)))
         kw.update(kwargs)
         print_fn = kw.pop("print_fn")
-        if print_fn is not None or filter_fn is not _accept_all:
+        from .data import UniqueFilter
+        on_device = filter_fn is _accept_all or isinstance(filter_fn, UniqueFilter)
+        if print_fn is not None or not on_device:
             # reference semantics on the materialised list; filter_fn is consulted lazily in
             # ascending (fun, index) order, which selects the same result as the reference's scan
             results = self.maxima(bounds, print_fn=print_fn, **kw)
@@ -142,7 +144,14 @@ class MaximizableMixin:
         if res is None:
             return OptimizeResult(x=X_init[i0], fun=f0, success=True)
         net = self._engine(X_init.shape[1])
-        key = int(net.select_best(res["fun"], res["status"]).item())
+        keep = None
+        if filter_fn is not _accept_all:
+            # the plugin's duplicate filter for every result in one launch (bore/data.py:42-48)
+            prev = filter_fn.stored()
+            if prev.shape[0] > 0:
+                keep = net.keep_unique_dev(res["x"].unsqueeze(0), net.to_device(prev[None], np.float64),
+                                           rtol=filter_fn.rtol, atol=filter_fn.atol).reshape(-1)
+        key = int(net.select_best(res["fun"], res["status"], keep_dev=keep).item())
         if key == 0:
             return None
         return self._result_at(res, 0x7fffffff - (key & 0x7fffffff))

@@ -16,13 +16,15 @@ largest budget <= b that already has ``num_random_init`` observations, BOHB-styl
 
 HpBandSter and ConfigSpace are used when installed, else the stand-ins in ``_compat``.
 """
+import logging
+
 import numpy as np
 
 from ._compat import HyperBand, base_config_generator
 from .types import DenseConfigurationSpace, array_from_dict, dict_from_array
 from ... import ops
 from ...base import maybe_distort
-from ...data import Record
+from ...data import Record, UniqueFilter
 from ...layers import BinaryCrossentropy, l2
 from ...math import steps_per_epoch
 from ...models import MaximizableDenseSequential
@@ -170,6 +172,22 @@ class ClassifierConfigGenerator(base_config_generator):
                          f"num steps per iter: {self.num_steps_per_iter}, "
                          f"num epochs: {num_epochs_per_iter}")
 
+    @property
+    def _print_fn(self):
+        """``print_fn=self.logger.debug`` as the reference passes it
+        (bore/plugins/hpbandster/base.py:263) -- but only while the logger would emit the
+        per-start lines; otherwise None, so that only the winner leaves the GPU."""
+        enabled = getattr(self.logger, "isEnabledFor", None)
+        if enabled is not None and not enabled(logging.DEBUG):
+            return None
+        return self.logger.debug
+
+    def _unique_filter(self):
+        """The reference passes ``filter_fn=self._is_unique`` (one Python callback per result);
+        ``UniqueFilter`` is the same predicate in a form ``argmax`` can evaluate for all results
+        in one launch when nothing has to be printed per start."""
+        return UniqueFilter(self.record, logger=self.logger)
+
     def _is_unique(self, res):
         is_duplicate = self.record.is_duplicate(res.x)
         if is_duplicate:
@@ -224,7 +242,7 @@ class ClassifierConfigGenerator(base_config_generator):
         opt = self.logit.argmax(self.bounds, num_starts=self.num_starts,
                                 num_samples=self.num_samples, method=self.method,
                                 options=dict(maxiter=self.max_iter, ftol=self.ftol),
-                                print_fn=self.logger.debug, filter_fn=self._is_unique,
+                                print_fn=self._print_fn, filter_fn=self._unique_filter(),
                                 random_state=self.random_state)
         if self.per_budget:
             self._budget_logits[b] = None if self.retrain else self.logit

@@ -206,7 +206,8 @@ int bore_select_best(const double *fun_dev, const int32_t *status_dev,
  *                                starts_per_model
  *   bore_select_best_groups      the scan of bore/mixins.py:80-87 per problem: keys_dev
  *                                [n_groups] int64, low 31 bits = 0x7fffffff - index within the
- *                                group, 0 when no start of the group qualifies               */
+ *                                group, 0 when no start of the group qualifies; keep_dev
+ *                                (may be NULL) [n_groups][per_group] is the filter_fn mask     */
 int bore_mlp_predict_multi(bore_mlp *h, int model0, int n_models, const float *X_dev,
                            int points_per_model, float *out_dev, void *stream);
 int bore_topk_smallest_groups(const float *f_dev, int n_groups, int per_group, int k, int negate,
@@ -218,8 +219,30 @@ int bore_lbfgsb_minimize_multi(bore_mlp *h, int model0, int n_models, int starts
                                double *x_dev, double *fun_dev, int32_t *nit_dev, int32_t *nfev_dev,
                                int32_t *status_dev, int32_t *task_dev, int *rounds_out,
                                long long *evals_out, void *stream);
-int bore_select_best_groups(const double *fun_dev, const int32_t *status_dev, int n_groups,
-                            int per_group, int64_t *keys_dev, int device, void *stream);
+int bore_select_best_groups(const double *fun_dev, const int32_t *status_dev,
+                            const uint8_t *keep_dev, int n_groups, int per_group, int64_t *keys_dev,
+                            int device, void *stream);
+
+/* ---- data step either side of the path --------------------
+ * bore_quantile_labels replaces Record.load_classification_data (bore/data.py:31-35) for
+ * n_problems target vectors y_dev [n_problems][N] (fp64) at once: tau = np.quantile(y, q)
+ * (method "linear": virtual index (N-1)*q, numpy's _lerp between the two neighbouring order
+ * statistics; NaN if the problem holds a NaN) and z = np.less(y, tau), STRICT.  Outputs (each
+ * may be NULL): z_f32_dev [n_problems][N] as 0.f/1.f (what bore_mlp_fit consumes), z_u8_dev the
+ * same as bytes, tau_dev [n_problems].  Bit-identical to numpy; N <= 16384 (one CTA sorts a
+ * problem's targets in shared memory).
+ * bore_is_duplicate replaces Record.is_duplicate (bore/data.py:42-48), the body of the
+ * plugin's filter_fn (bore/plugins/hpbandster/base.py:227-231): candidate c of group g
+ * (x_dev [n_groups][per_group][D]) is a duplicate if np.allclose(x_prev, x, rtol, atol) holds for
+ * any of the group's stored rows x_prev_dev [n_groups][n_prev][D], i.e. for every coordinate
+ * |x_prev - x| <= atol + rtol*|x| (x finite) or x_prev == x.  dup_dev / keep_dev (each may be
+ * NULL) receive the flag / its negation per candidate; keep_dev is the mask bore_select_best
+ * and bore_select_best_groups take.                                                       */
+int bore_quantile_labels(const double *y_dev, int n_problems, int N, double q, float *z_f32_dev,
+                         uint8_t *z_u8_dev, double *tau_dev, int device, void *stream);
+int bore_is_duplicate(const double *x_dev, int n_groups, int per_group, const double *x_prev_dev,
+                      int n_prev, int D, double rtol, double atol, uint8_t *dup_dev,
+                      uint8_t *keep_dev, int device, void *stream);
 
 /* ---- measurement helper -----------------------------------------------------------------
  * FP32 FFMA-only microbenchmark (register-resident FMA chains, all SMs): the measured

@@ -119,7 +119,51 @@ def fit_golden():
     print("fit_golden.npz written")
 
 
+def data_step_golden():
+    """Quantile labels and duplicate flags produced by the reference's own bore.data.Record
+    (importable: numpy only) -- the known answers of the device data step (data.cu)."""
+    sys.path.insert(0, "/root/reference")
+    from bore.data import Record                                 # noqa: E402
+    out = dict(numpy_version=np.array(np.__version__),
+               source=np.array("bore.data.Record of ltiao/bore v1.5.0, imported from /root/reference"))
+    cases = []
+    for ci, (seed, M, N, D, gamma) in enumerate(((0, 5, 1, 2, 0.25), (1, 4, 2, 3, 1 / 3), (2, 6, 37, 6, 0.25),
+                                                 (3, 3, 64, 50, 0.5), (4, 4, 500, 6, 0.25), (5, 2, 2000, 3, 1 / 3),
+                                                 (6, 3, 110, 2, 0.0), (7, 3, 129, 2, 1.0), (8, 3, 1000, 4, 0.9))):
+        rs = np.random.RandomState(seed)
+        X = rs.uniform(size=(M, N, D))
+        y = rs.normal(size=(M, N))
+        if N > 4:
+            y[:, :3] = y[:, :1]                       # ties
+            y[0] = np.round(y[0], 1)                  # many repeated values around the threshold
+            y[-1, 1] = -0.0; y[-1, 2] = 0.0
+        K = 7
+        cand = rs.uniform(size=(M, K, D))
+        cand[:, 0] = X[:, 0]                           # exact duplicate
+        cand[:, 1] = X[:, -1] * (1 + 5e-6)             # within rtol
+        cand[:, 2] = X[:, N // 2] + 1e-9               # within atol-ish
+        cand[:, 3] = X[:, 0] + 1e-4                    # outside
+        cand[:, 4, 0] = X[:, 0, 0]                     # one coordinate equal only
+        z = np.zeros((M, N), bool); dup = np.zeros((M, K), bool)
+        for m in range(M):
+            rec = Record()
+            for xi, yi in zip(X[m], y[m]):
+                rec.append(x=xi, y=yi)
+            _, z[m] = rec.load_classification_data(gamma)
+            dup[m] = [rec.is_duplicate(c) for c in cand[m]]
+        for k, v in dict(X=X, y=y, gamma=np.array(gamma), z=z, cand=cand, dup=dup).items():
+            out[f"c{ci}/{k}"] = v
+        cases.append(ci)
+    out["cases"] = np.array(cases)
+    np.savez_compressed(os.path.join(HERE, "data_step_golden.npz"), **out)
+    print("data_step_golden.npz written")
+
+
 if __name__ == "__main__":
+    if "--data-step" in sys.argv:
+        data_step_golden()
+        sys.exit(0)
     host_golden()
+    data_step_golden()
     lbfgsb_golden()
     fit_golden()
