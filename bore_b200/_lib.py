@@ -65,6 +65,14 @@ SIGNATURES = {
     "bore_quantile_labels": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, vp, vp, vp, C.c_int, vp]),
     "bore_is_duplicate": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_double, C.c_double,
                                     vp, vp, C.c_int, vp]),
+    "bore_svgd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "bore_svgd_maximize": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_double, C.c_int,
+                                     C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                     vp, C.c_size_t, vp]),
+    "bore_svgd_step": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_double, C.c_int,
+                                 C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                 vp, vp, C.c_int, vp]),
+    "bore_svgd_kernel_value_and_grad": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, vp, vp, C.c_int, vp]),
     "bore_bench_ffma_peak": (C.c_int, [C.c_int, C.c_int, c_double_p]),
 }
 

@@ -379,6 +379,33 @@ class NativeMLP:
                                               None, _ptr(keep), self.device, self._stream()))
         return keep
 
+    # ------------------------------------------------------------------ SVGD (section 8f row 3)
+    def svgd_maximize(self, x_init, transform, low, high, n_iter, length_scale, step_size, alpha, eps,
+                      tau, lambd, zeta_c, model0=0):
+        """x_init (n, D) or (P, n, D) float64 -> particles after n_iter SVGD iterations on
+        transform(model(x)) (maximised), model model0+p for block p; the whole loop is enqueued
+        at once (bore_svgd_maximize)."""
+        torch = _torch()
+        x = np.asarray(x_init, np.float64)
+        single = x.ndim == 2
+        x3 = x[None] if single else x
+        P, n, D = x3.shape
+        assert D == self.D and model0 + P <= self.n_models
+        x_dev = self.to_device(x3, np.float64).clone()
+        nbytes = self.lib.bore_svgd_workspace_bytes(P, n, D)
+        work = torch.empty(int(nbytes), dtype=torch.uint8, device=self._tdev())
+        lo = hi = None
+        if low is not None:
+            lo = np.ascontiguousarray(np.broadcast_to(np.asarray(low, np.float64), (D,)))
+            hi = np.ascontiguousarray(np.broadcast_to(np.asarray(high, np.float64), (D,)))
+        _lib.check(self.lib.bore_svgd_maximize(
+            self.h, int(model0), int(P), TRANSFORM_CODES[transform], _ptr(x_dev), int(n),
+            _np_ptr(lo) if lo is not None else None, _np_ptr(hi) if hi is not None else None,
+            float(length_scale), int(n_iter), float(step_size), float(alpha), float(eps), float(tau),
+            float(lambd), float(zeta_c), _ptr(work), work.numel(), self._stream()))
+        out = x_dev.cpu().numpy()
+        return out[0] if single else out
+
     # ------------------------------------------------------------------ K1
     def fit_dev(self, X_dev, z_dev, N, batch_size, epochs, perm_dev, loss_dev=None,
                 model0=0, count=1, shared_data=True, shared_perm=True):
@@ -433,3 +460,65 @@ def ffma_peak_tflops(device=0, iters=4096):
     out = C.c_double()
     _lib.check(lib.bore_bench_ffma_peak(int(device), int(iters), C.byref(out)))
     return out.value
+
+
+# ---------------------------------------------------------------------- SVGD without a model handle
+def _current_device():
+    lib = _lib.require_cuda()
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise _lib.BoreNativeError("torch sees no CUDA device; bore_b200 has no CPU fallback")
+    dev = torch.cuda.current_device()
+    return lib, torch, dev, torch.device("cuda", dev), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def svgd_kernel_value_and_grad(X, length_scale):
+    """RadialBasis.value_and_grad on the device: X (n, D) float64 -> K (n, n), K_grad (n, D)."""
+    lib, torch, dev, tdev, stream = _current_device()
+    X = np.ascontiguousarray(X, np.float64)
+    n, D = X.shape
+    x_dev = torch.from_numpy(X).to(tdev)
+    K = torch.empty(n, n, dtype=torch.float64, device=tdev)
+    Kg = torch.empty(n, D, dtype=torch.float64, device=tdev)
+    ls = float("nan") if length_scale is None else float(length_scale)
+    _lib.check(lib.bore_svgd_kernel_value_and_grad(_ptr(x_dev), n, D, ls, _ptr(K), _ptr(Kg), dev, stream))
+    return K.cpu().numpy(), Kg.cpu().numpy()
+
+
+class SvgdStepper:
+    """Device-resident SVGD state (particles + AdaGrad accumulator) advanced one iteration at a
+    time with a caller-supplied ``f, f_grad`` (bore_svgd_step) -- for objectives that are not a
+    bore_b200 model (the reference's SVGD accepts any callable, svgd/base.py:78)."""
+
+    def __init__(self, x_init, low, high, length_scale, step_size, alpha, eps, tau, lambd, zeta_c):
+        self.lib, torch, self.dev, tdev, _ = _current_device()
+        x = np.ascontiguousarray(x_init, np.float64)
+        assert x.ndim == 2
+        self.n, self.D = x.shape
+        self._x = torch.from_numpy(x).to(tdev)
+        self._hist = torch.zeros_like(self._x)
+        self._lo = self._hi = None
+        if low is not None:
+            D = self.D
+            self._lo = torch.from_numpy(np.array(np.broadcast_to(np.asarray(low, np.float64), (D,)))).to(tdev)
+            self._hi = torch.from_numpy(np.array(np.broadcast_to(np.asarray(high, np.float64), (D,)))).to(tdev)
+        self._opts = (float(length_scale), float(step_size), float(alpha), float(eps), float(tau),
+                      float(lambd), float(zeta_c))
+        self._it = 0
+        self._tdev = tdev
+
+    def x(self):
+        return self._x.cpu().numpy()
+
+    def step(self, f, f_grad):
+        torch = _torch()
+        f = np.ascontiguousarray(np.broadcast_to(f, (self.n,)), np.float64)
+        g = np.ascontiguousarray(f_grad, np.float64)
+        assert g.shape == (self.n, self.D)
+        f_dev, g_dev = torch.from_numpy(f).to(self._tdev), torch.from_numpy(g).to(self._tdev)
+        ls, step, alpha, eps, tau, lambd, zc = self._opts
+        stream = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        _lib.check(self.lib.bore_svgd_step(_ptr(self._x), 1, self.n, self.D, _ptr(f_dev), _ptr(g_dev), 1,
+                                           _ptr(self._lo), _ptr(self._hi), ls, self._it, step, alpha, eps,
+                                           tau, lambd, zc, _ptr(self._hist), None, self.dev, stream))
+        self._it += 1

@@ -6,7 +6,8 @@ moves to the device:
     X_init (host MT19937, as the reference)  ->  K0 predict  ->  K4 top-k  ->  K3 batched
     L-BFGS-B with K2 inlined as the objective  ->  K4 first-minimum selection
 
-``BatchMaximizableMixin`` (SVGD, bore/mixins.py:92-116) is out of scope.
+``BatchMaximizableMixin`` (bore/mixins.py:92-116) adds the SVGD batch argmax, whose iterations
+run on the device as well (csrc/svgd.cu).
 """
 import numpy as np
 from scipy.optimize import OptimizeResult
@@ -198,3 +199,22 @@ class MaximizableMixin:
         out = self._result_from_record(rec.cpu().numpy(), D)
         out["global_index"] = gidx
         return out
+
+
+class BatchMaximizableMixin(MaximizableMixin):
+    """Adds ``argmax_batch``: a batch of maximisers by SVGD (bore/mixins.py:92-116)."""
+
+    def __init__(self, transform=ops.identity, *args, **kwargs):
+        super(BatchMaximizableMixin, self).__init__(transform=transform, *args, **kwargs)
+        # maximization problem for SVGD (bore/mixins.py:97-98)
+        self._func_max = convert(self, transform=transform)
+
+    def argmax_batch(self, batch_size, bounds, length_scale=None, n_iter=1000, step_size=1e-3,
+                     alpha=.9, eps=1e-6, tau=1.0, lambd=None, random_state=None):
+        from .optimizers.svgd.base import SVGD, DistortionConstant, DistortionExpDecay
+        from .optimizers.svgd.kernels import RadialBasis
+        distortion = DistortionConstant() if lambd is None else DistortionExpDecay(lambd=lambd)
+        kernel = RadialBasis(length_scale=length_scale)
+        svgd = SVGD(kernel=kernel, n_iter=n_iter, step_size=step_size, alpha=alpha, eps=eps, tau=tau,
+                    distortion=distortion)
+        return svgd.optimize(self._func_max, batch_size, bounds=bounds, random_state=random_state)

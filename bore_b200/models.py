@@ -13,7 +13,7 @@ import numpy as np
 
 from . import ops
 from .layers import Dense, BinaryCrossentropy, Adam
-from .mixins import MaximizableMixin
+from .mixins import MaximizableMixin, BatchMaximizableMixin
 
 
 class History:
@@ -213,6 +213,13 @@ class Sequential:
     def _native_value_and_grad(self, X, transform, negate):
         return self._engine(X.shape[1]).value_and_grad(X, transform, negate)
 
+    def _native_svgd(self, x_init, transform_fn, low, high, n_iter, opts):
+        """SVGD on ``transform_fn(model(x))`` (maximised) with the whole loop on the device."""
+        e = transform_fn(ops.Expr(self, (1,), (1,)))
+        if not isinstance(e, ops.Expr) or e.sign != 1:
+            raise NotImplementedError("transform must be one of bore_b200.ops.identity/sigmoid/exp")
+        return self._engine(x_init.shape[-1]).svgd_maximize(x_init, e.transform, low, high, n_iter, **opts)
+
 
 Model = Sequential
 
@@ -243,4 +250,16 @@ class MaximizableSequential(MaximizableMixin, Sequential):
 
 
 class MaximizableDenseSequential(MaximizableMixin, DenseSequential):
+    pass
+
+
+class BatchMaximizableModel(BatchMaximizableMixin, Model):
+    pass
+
+
+class BatchMaximizableSequential(BatchMaximizableMixin, Sequential):
+    pass
+
+
+class BatchMaximizableDenseSequential(BatchMaximizableMixin, DenseSequential):
     pass

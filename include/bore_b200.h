@@ -244,6 +244,33 @@ int bore_is_duplicate(const double *x_dev, int n_groups, int per_group, const do
                       int n_prev, int D, double rtol, double atol, uint8_t *dup_dev,
                       uint8_t *keep_dev, int device, void *stream);
 
+/* ---- batch argmax by SVGD ---------------------------------
+ * Replaces BatchMaximizableMixin.argmax_batch (bore/mixins.py:100-116), i.e.
+ * SVGD.optimize_from_init (bore/optimizers/svgd/base.py:78-118) with RadialBasis
+ * (svgd/kernels.py:13-28), for n particles per problem, x_dev [n_problems][n][D] fp64 in/out.
+ *   length_scale  NaN = None: median heuristic sqrt(.5 * median(r2) / log(n + 1)); floored at 1e-6
+ *   lambd         NaN = DistortionConstant(zeta_c); else DistortionExpDecay: rank(f) ** -lambd
+ *   step_size, alpha, eps, tau: SVGD.__init__ (svgd/base.py:69-70)
+ * bore_svgd_maximize runs n_iter iterations with the handle's model(s) as `func`
+ * (transform(model(x)), maximised: `self._func_max`, bore/mixins.py:98) -- two launches per
+ * iteration, no host round trip; lo_host / hi_host (both or neither) clip every iterate.
+ * bore_svgd_step is ONE iteration for a caller-supplied objective: f_dev [n_problems][n] and
+ * g_dev [n_problems][n][D] hold func(x) as fp32 or fp64 (fg_is_f64); `iteration` == 0 starts the
+ * AdaGrad accumulator hist_dev [n_problems][n][D]; x32_dev (may be NULL) receives an fp32 copy
+ * of the new x.
+ * bore_svgd_kernel_value_and_grad is RadialBasis.value_and_grad alone: K [n][n], K_grad [n][D]. */
+size_t bore_svgd_workspace_bytes(int n_problems, int n, int D);
+int bore_svgd_maximize(bore_mlp *h, int model0, int n_problems, int transform, double *x_dev, int n,
+                       const double *lo_host, const double *hi_host, double length_scale, int n_iter,
+                       double step_size, double alpha, double eps, double tau, double lambd,
+                       double zeta_c, void *work_dev, size_t work_bytes, void *stream);
+int bore_svgd_step(double *x_dev, int n_problems, int n, int D, const void *f_dev, const void *g_dev,
+                   int fg_is_f64, const double *lo_dev, const double *hi_dev, double length_scale,
+                   int iteration, double step_size, double alpha, double eps, double tau, double lambd,
+                   double zeta_c, double *hist_dev, float *x32_dev, int device, void *stream);
+int bore_svgd_kernel_value_and_grad(const double *x_dev, int n, int D, double length_scale,
+                                    double *K_dev, double *Kgrad_dev, int device, void *stream);
+
 /* ---- measurement helper -----------------------------------------------------------------
  * FP32 FFMA-only microbenchmark (register-resident FMA chains, all SMs): the measured
  * denominator for the FP32 roofline, since MEASURED_PEAKS.json carries only HBM and BF16.

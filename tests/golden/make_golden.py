@@ -159,11 +159,92 @@ def data_step_golden():
     print("data_step_golden.npz written")
 
 
+def svgd_golden():
+    """Kernel values and SVGD trajectories produced by the reference's own
+    bore.optimizers.svgd (importable: numpy / scipy / sklearn only)."""
+    sys.path.insert(0, "/root/reference")
+    from bore.optimizers.svgd.base import SVGD, DistortionConstant, DistortionExpDecay   # noqa: E402
+    from bore.optimizers.svgd.kernels import RadialBasis                                   # noqa: E402
+    from oracle import svgd as osv
+    from helpers import NETS, trained_weights
+    out = dict(numpy_version=np.array(np.__version__),
+               source=np.array("bore.optimizers.svgd of ltiao/bore v1.5.0, imported from /root/reference"))
+    # (1) the kernel alone -- the grid of the reference's tests/test_optimizers.py:76-127
+    kc = 0
+    for n in (1, 2, 4, 16, 33):
+        for D in (1, 2, 64):
+            for ls in (None, 1e-3, 0.5, 2.0):
+                X = np.random.RandomState(42 + kc).rand(n, D)
+                if n >= 4:
+                    X[1] = X[0]                       # coincident particles: zeros off the diagonal
+                K, Kg = RadialBasis(length_scale=ls).value_and_grad(X)
+                out[f"k{kc}/X"] = X; out[f"k{kc}/K"] = K; out[f"k{kc}/Kg"] = Kg
+                out[f"k{kc}/ls"] = np.array(np.nan if ls is None else ls)
+                kc += 1
+    out["n_kernel_cases"] = np.array(kc)
+    # (2) SVGD on the reference test's own target (tests/test_optimizers.py:130-160): analytic func
+    mu = np.array([-0.6871, 0.8010])
+    precision = np.array([[0.2260, 0.1652], [0.1652, 0.6779]])
+
+    def func(x):
+        d = x - mu
+        return -0.5 * np.einsum("ni,ij,nj->n", d, precision, d), (mu - x) @ precision
+    tc = 0
+    for n_iter, n, ls, lambd, seed in ((50, 4, None, None, 42), (50, 16, 0.5, None, 8888), (200, 16, None, 0.5, 42),
+                                       (500, 64, None, None, 42), (200, 7, 1.0, 2.0, 8888), (100, 2, None, None, 1),
+                                       (100, 1, None, None, 1)):
+        rs = np.random.RandomState(seed)
+        x_init = rs.randn(n, 2)
+        bounds = [(-3., 3.), (-2., 4.)]
+        snaps = []
+        dist = DistortionConstant() if lambd is None else DistortionExpDecay(lambd=lambd)
+        svgd = SVGD(kernel=RadialBasis(length_scale=ls), n_iter=n_iter, step_size=1e-2, alpha=.9, eps=1e-6,
+                    tau=1.0, distortion=dist)
+        x = svgd.optimize_from_init(func, x_init, bounds=bounds, callback=lambda v: snaps.append(v.copy()))
+        out[f"t{tc}/x_init"] = x_init; out[f"t{tc}/x"] = x
+        keep = [i for i in (0, 1, 9, 49, 99, 199, 499) if i < n_iter]
+        out[f"t{tc}/snap_iters"] = np.array(keep); out[f"t{tc}/snaps"] = np.stack([snaps[i] for i in keep])
+        out[f"t{tc}/cfg"] = np.array([n_iter, n, np.nan if ls is None else ls, np.nan if lambd is None else lambd])
+        tc += 1
+    out["n_analytic_cases"] = np.array(tc)
+    # (3) SVGD with the model closure as func (bore/mixins.py:98,115): the reference's SVGD class driven
+    #     by the oracle MLP's value-and-gradient (fp32), trained weights
+    mc = 0
+    for name, n, n_iter, ls, lambd in (("cfg2_hartmann6", 16, 100, None, None), ("cfg5_plugin8", 8, 60, None, 1.0),
+                                       ("cfg3_ackley50", 32, 40, None, None), ("cfg1_branin", 64, 200, 0.2, None)):
+        dims, acts, transform = NETS[name]
+        w = trained_weights(dims, acts, seed=31)
+        D = dims[0]
+        rs = np.random.RandomState(5)
+        bounds = [(0., 1.)] * D
+        x_init = rs.uniform(size=(n, D))
+        snaps = []
+        dist = DistortionConstant() if lambd is None else DistortionExpDecay(lambd=lambd)
+        svgd = SVGD(kernel=RadialBasis(length_scale=ls), n_iter=n_iter, step_size=1e-3, alpha=.9, eps=1e-6,
+                    tau=1.0, distortion=dist)
+        x = svgd.optimize_from_init(osv.make_func_max(w, acts, transform), x_init, bounds=bounds,
+                                    callback=lambda v: snaps.append(v.copy()))
+        out[f"m{mc}/name"] = np.array(name); out[f"m{mc}/x_init"] = x_init; out[f"m{mc}/x"] = x
+        keep = [i for i in (0, 1, 9, 39, 59, 99, 199) if i < n_iter]
+        out[f"m{mc}/snap_iters"] = np.array(keep); out[f"m{mc}/snaps"] = np.stack([snaps[i] for i in keep])
+        out[f"m{mc}/cfg"] = np.array([n_iter, n, np.nan if ls is None else ls, np.nan if lambd is None else lambd])
+        for i, wi in enumerate(w):
+            out[f"m{mc}/w{i}"] = wi
+        mc += 1
+    out["n_model_cases"] = np.array(mc)
+    np.savez_compressed(os.path.join(HERE, "svgd_golden.npz"), **out)
+    print("svgd_golden.npz written")
+
+
 if __name__ == "__main__":
+    if "--svgd" in sys.argv:
+        svgd_golden()
+        sys.exit(0)
     if "--data-step" in sys.argv:
         data_step_golden()
         sys.exit(0)
     host_golden()
     data_step_golden()
+    svgd_golden()
     lbfgsb_golden()
     fit_golden()
