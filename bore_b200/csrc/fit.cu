@@ -53,27 +53,37 @@ struct FitPlan {
   int w[BORE_MAX_LAYERS];    // W_l  [in][JP]          (all Dense layers incl. final)
   int wt[BORE_MAX_LAYERS];   // W_l^T [out][KP]        (layers 1.. only: layer 0 needs no reverse)
   int b[BORE_MAX_LAYERS];    // bias [JP]
+  int JP[BORE_MAX_LAYERS], KP[BORE_MAX_LAYERS];  // leading dimensions of W_l / W_l^T
+  int ks[BORE_MAX_LAYERS];   // sample-split of layer l's weight-gradient pass (0: the tile owner
+                             // applies Adam straight from registers, no scratch)
   int h[BORE_MAX_LAYERS + 1];// activations [dim][BS]; h[0] = input batch
   int dl[2];                 // delta ping/pong [maxw][BS]
   int zb;                    // labels [BS]
   int red;                   // reduction scratch [32]
   int idx;                   // gathered row indices [BS] (ints)
+  int gs;                    // gradient partials [ks][in*out + out] of the layer in flight
   int total;                 // floats
   int BS;
 };
 
 __host__ __device__ inline int r4(int a) { return (a + 3) & ~3; }
 
-__host__ __device__ inline void make_fit_plan(const MlpDesc &d, int batch, FitPlan &p) {
+// `threads`: CTA size the plan is made for (the sample-split of the gradient passes spreads
+// each layer's tiles over all of them); smem_limit: floats available, splits are dropped if the
+// gradient scratch does not fit
+__host__ __device__ inline void make_fit_plan(const MlpDesc &d, int batch, int threads, int smem_limit,
+                                              FitPlan &p) {
   const int L = d.n_layers;
   int BS = r4(batch) + 4;
   p.BS = BS;
   int off = 0, maxw = 1;
   for (int l = 0; l < L; ++l) {
     const int in = d.dims[l], out = d.dims[l + 1];
-    p.w[l] = off; off += in * r4(out);
-    p.b[l] = off; off += r4(out);
-    p.wt[l] = off; if (l > 0) off += out * r4(in);
+    p.JP[l] = r4(out);
+    p.KP[l] = r4(in) + 4;  // +4: the Adam pass writes W^T with consecutive j (stride KP) per lane
+    p.w[l] = off; off += in * p.JP[l];
+    p.b[l] = off; off += p.JP[l];
+    p.wt[l] = off; if (l > 0) off += out * p.KP[l];
     if (out > maxw) maxw = out;
   }
   for (int l = 0; l <= L; ++l) { p.h[l] = off; off += d.dims[l] * BS; }
@@ -82,6 +92,30 @@ __host__ __device__ inline void make_fit_plan(const MlpDesc &d, int batch, FitPl
   p.zb = off; off += BS;
   p.red = off; off += 32;
   p.idx = off; off += BS;
+  // sample-split per layer: as many splits (power of two) as leave every thread at most one
+  // partial tile, each split at least one 4-sample chunk
+  const int nchunk = r4(batch) / 4;
+  int gmax = 0;
+  for (int l = 0; l < L; ++l) {
+    const int in = d.dims[l], out = d.dims[l + 1];
+    const int items = out == 1 ? in : ((in + 3) / 4) * (p.JP[l] / 4);
+    int ks = 1;
+    while (items * ks * 2 <= threads && ks * 2 <= nchunk && ks < 16) ks *= 2;
+    if (out > 1 && ks == 1) ks = 0;  // enough tiles already: direct path
+    p.ks[l] = ks;
+    const int need = ks * (in * out + out);
+    if (need > gmax) gmax = need;
+  }
+  if (off + r4(gmax) > smem_limit) {  // big nets: keep only the (tiny) scratch of 1-unit layers
+    gmax = 0;
+    for (int l = 0; l < L; ++l) {
+      const int in = d.dims[l], out = d.dims[l + 1];
+      if (out > 1) p.ks[l] = 0;
+      const int need = p.ks[l] * (in * out + out);
+      if (need > gmax) gmax = need;
+    }
+  }
+  p.gs = off; off += r4(gmax);
   p.total = r4(off);
 }
 
@@ -113,6 +147,48 @@ __device__ __forceinline__ float block_sum(float v, float *red) {
   return t;
 }
 
+// Keras-form Adam on one parameter (eps outside the bias correction); returns the new value.
+// sqrt.approx / div.approx (<= 2 ulp each): the IEEE forms cost ~25 instructions per parameter,
+// a fifth of the whole kernel at Dense32 sizes, for digits far below fp32 re-association noise.
+__device__ __forceinline__ float adam_update(float wv, float g, float &m, float &v, float om1, float om2,
+                                             float alpha, float eps) {
+  m += (g - m) * om1;
+  v += (g * g - v) * om2;
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return wv - __fdividef(m * alpha, r + eps);
+}
+
+// e / n for 0 <= e < 2^20 through a precomputed reciprocal (inv = 1.f / n): exact, the offset .5
+// keeps the product away from integer boundaries
+__device__ __forceinline__ int fdiv(int e, float inv) { return __float2int_rz(((float)e + 0.5f) * inv); }
+
+// acc[i][u] += sum_k A[k*lda + i] * B[k*ldb + u]: the 4 x 4 register tile of every GEMM below
+__device__ __forceinline__ void tile_fma(const float *__restrict__ ap, int lda, const float *__restrict__ bp,
+                                         int ldb, int K, float (&acc)[4][4]) {
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float4 av = *reinterpret_cast<const float4 *>(ap + k * lda);
+    const float4 wv = *reinterpret_cast<const float4 *>(bp + k * ldb);
+    const float a4[4] = {av.x, av.y, av.z, av.w};
+    const float w4[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[i][u] = fmaf(a4[i], w4[u], acc[i][u]);
+  }
+}
+
+// Phases of one minibatch step (all inside the CTA, barrier between phases):
+//   gather | forward l = 0..L-1 | loss, dL/dlogit | for l = L-1..0: { delta_{l-1} AND the partial
+//   weight gradients of layer l, side by side } , { Adam on layer l }.
+// Every phase spreads its work over ALL threads: a layer's gradient tiles are split over the
+// sample dimension (FitPlan::ks) until there is one partial tile per thread, the partials meet
+// in a shared-memory scratch, and the Adam pass walks the layer's parameters one per thread in
+// flat (Keras) order, so its Adam-slot traffic is coalesced.  1-unit layers (the output layer)
+// use dot-product forms instead of 4x4 tiles padded with zeros.  (The first version gave every
+// 4x4 gradient tile to one thread: with Dense32 layers 64 / 16 / 8 of 128 threads worked while
+// the rest waited at the barrier -- 44 % of all stall samples, profiles/r01_notes.md.)
 __global__ void __launch_bounds__(FIT_THREADS) fit_kernel(const FitArgs a) {
   extern __shared__ __align__(16) float sm[];
   const MlpDesc &d = a.d;
@@ -128,11 +204,12 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_kernel(const FitArgs a) {
   const int *perm = a.perm + (a.shared_perm ? 0 : (size_t)blockIdx.x * a.epochs * a.N);
   int *idxb = reinterpret_cast<int *>(sm + P.idx);
   float *red = sm + P.red;
+  float *gs = sm + P.gs;
   const int D = d.dims[0];
 
   // ---- stage the weights: W_l [in][JP], W_l^T [out][KP] (l>0), bias ----
   for (int l = 0; l < L; ++l) {
-    const int in = d.dims[l], out = d.dims[l + 1], JP = r4(out), KP = r4(in);
+    const int in = d.dims[l], out = d.dims[l + 1], JP = P.JP[l], KP = P.KP[l];
     for (int e = tid; e < in * JP; e += NT) {
       const int k = e / JP, j = e - k * JP;
       sm[P.w[l] + e] = j < out ? gp[d.w_off[l] + k * out + j] : 0.f;
@@ -145,6 +222,9 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_kernel(const FitArgs a) {
       }
   }
   long long t_step = a.adam_t[model];
+  // beta^t as running products in fp64 (one multiplication per step instead of two powf calls)
+  double b1p_d = pow((double)a.beta1, (double)t_step), b2p_d = pow((double)a.beta2, (double)t_step);
+  const float inv_D = 1.f / (float)D;
   __syncthreads();
 
   const int steps_per_epoch = (a.N + a.batch - 1) / a.batch;
@@ -153,7 +233,8 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_kernel(const FitArgs a) {
     for (int st = 0; st < steps_per_epoch; ++st) {
       const int s0 = st * a.batch;
       const int nb = min(a.batch, a.N - s0);
-      const int BP = r4(nb);
+      const int BP = r4(nb), nchunk = BP >> 2;
+      const float inv_nchunk = 1.f / (float)nchunk;
       // ---- gather the minibatch (transposed) ----
       for (int p = tid; p < BP; p += NT) {
         const int row = p < nb ? perm[(size_t)ep * a.N + s0 + p] : -1;
@@ -162,7 +243,7 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_kernel(const FitArgs a) {
       }
       __syncthreads();
       for (int e = tid; e < BP * D; e += NT) {
-        const int p = e / D, k = e - p * D;
+        const int p = fdiv(e, inv_D), k = e - p * D;
         const int row = idxb[p];
         sm[P.h[0] + k * BS + p] = row >= 0 ? X[(size_t)row * D + k] : 0.f;
       }
@@ -170,40 +251,59 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_kernel(const FitArgs a) {
 
       // ---- forward ----
       for (int l = 0; l < L; ++l) {
-        const int in = d.dims[l], out = d.dims[l + 1], JP = r4(out);
+        const int in = d.dims[l], out = d.dims[l + 1], JP = P.JP[l];
         const float *A = sm + P.h[l];
         const float *W = sm + P.w[l];
         const float *bs = sm + P.b[l];
         float *H = sm + P.h[l + 1];
         const int act = (l == L - 1) ? BORE_ACT_LINEAR : d.act[l];  // loss works on the logit
-        const int tpn = BP / 4, ntile = tpn * (JP / 4);
-        for (int tt = tid; tt < ntile; tt += NT) {
-          const int tp = tt % tpn, tj = tt / tpn;
-          float acc[4][4] = {};
-          const float *ap = A + tp * 4;
-          const float *wp = W + tj * 4;
-#pragma unroll 4
-          for (int k = 0; k < in; ++k) {
-            const float4 av = *reinterpret_cast<const float4 *>(ap + k * BS);
-            const float4 wv = *reinterpret_cast<const float4 *>(wp + k * JP);
-            const float a4[4] = {av.x, av.y, av.z, av.w};
-            const float w4[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-              for (int u = 0; u < 4; ++u) acc[i][u] = fmaf(a4[i], w4[u], acc[i][u]);
+        if (out == 1) {
+          // u[p] = b + sum_k h[k][p] w[k]: one 4-sample chunk per group of kf adjacent lanes,
+          // k interleaved over the group, partial sums combined by shuffle
+          int kf = 1;
+          while (kf < 8 && nchunk * kf * 2 <= NT) kf *= 2;
+          const int per_pass = NT / kf;
+          for (int base = 0; base < nchunk; base += per_pass) {
+            const int c = base + tid / kf, s = tid & (kf - 1);
+            const bool valid = c < nchunk;
+            const float *ap = A + 4 * (valid ? c : 0);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = s; k < in; k += kf) {
+              const float4 av = *reinterpret_cast<const float4 *>(ap + k * BS);
+              const float w = W[k * JP];
+              acc.x = fmaf(av.x, w, acc.x); acc.y = fmaf(av.y, w, acc.y);
+              acc.z = fmaf(av.z, w, acc.z); acc.w = fmaf(av.w, w, acc.w);
+            }
+            for (int o = kf >> 1; o > 0; o >>= 1) {
+              acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+              acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+              acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+              acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+            }
+            if (valid && s == 0) {
+              const float b = bs[0];
+              *reinterpret_cast<float4 *>(H + 4 * c) = make_float4(f_act(act, acc.x + b), f_act(act, acc.y + b),
+                                                                   f_act(act, acc.z + b), f_act(act, acc.w + b));
+            }
           }
+        } else {
+          const int ntile = nchunk * (JP / 4);
+          for (int tt = tid; tt < ntile; tt += NT) {
+            const int tj = fdiv(tt, inv_nchunk), tp = tt - tj * nchunk;
+            float acc[4][4] = {};
+            tile_fma(A + tp * 4, BS, W + tj * 4, JP, in, acc);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int j = tj * 4 + u;
-            if (j < out) {
-              const float b = bs[j];
-              float4 o;
-              o.x = f_act(act, acc[0][u] + b);
-              o.y = f_act(act, acc[1][u] + b);
-              o.z = f_act(act, acc[2][u] + b);
-              o.w = f_act(act, acc[3][u] + b);
-              *reinterpret_cast<float4 *>(H + j * BS + tp * 4) = o;
+            for (int u = 0; u < 4; ++u) {
+              const int j = tj * 4 + u;
+              if (j < out) {
+                const float b = bs[j];
+                float4 o;
+                o.x = f_act(act, acc[0][u] + b);
+                o.y = f_act(act, acc[1][u] + b);
+                o.z = f_act(act, acc[2][u] + b);
+                o.w = f_act(act, acc[3][u] + b);
+                *reinterpret_cast<float4 *>(H + j * BS + tp * 4) = o;
+              }
             }
           }
         }
@@ -230,7 +330,9 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_kernel(const FitArgs a) {
 
       // ---- Adam scalars for this step (Keras: t starts at 1) ----
       t_step += 1;
-      const float b1p = powf(a.beta1, (float)t_step), b2p = powf(a.beta2, (float)t_step);
+      b1p_d *= (double)a.beta1;
+      b2p_d *= (double)a.beta2;
+      const float b1p = (float)b1p_d, b2p = (float)b2p_d;
       const float alpha = a.lr * sqrtf(1.f - b2p) / (1.f - b1p);
       const float om1 = 1.f - a.beta1, om2 = 1.f - a.beta2;
       float reg = 0.f;
@@ -238,51 +340,173 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_kernel(const FitArgs a) {
       // ---- reverse + update, top layer first ----
       int cur = 0;
       for (int l = L - 1; l >= 0; --l) {
-        const int in = d.dims[l], out = d.dims[l + 1], JP = r4(out), KP = r4(in);
+        const int in = d.dims[l], out = d.dims[l + 1], JP = P.JP[l], KP = P.KP[l];
+        const float inv_out = 1.f / (float)out;
         const float *DL = sm + P.dl[cur];  // delta_l [out][BS]
+        const float *Hin = sm + P.h[l];    // input of layer l = output of layer l-1
+        const int ks = P.ks[l];
+        const int psz = in * out + out;    // layer l's parameters, flat: W_l then b_l
         // (1) delta_{l-1} = (delta_l W_l^T) . act'(h_{l-1}) into the other buffer
         if (l > 0) {
           const float *WT = sm + P.wt[l];
-          const float *Hin = sm + P.h[l];
           float *DN = sm + P.dl[cur ^ 1];
           const int actp = d.act[l - 1];
-          const int tpn = BP / 4, ntile = tpn * (KP / 4);
-          for (int tt = tid; tt < ntile; tt += NT) {
-            const int tp = tt % tpn, tk = tt / tpn;
-            float acc[4][4] = {};
-            const float *ap = DL + tp * 4;
-            const float *wp = WT + tk * 4;
-#pragma unroll 4
-            for (int j = 0; j < out; ++j) {
-              const float4 av = *reinterpret_cast<const float4 *>(ap + j * BS);
-              const float4 wv = *reinterpret_cast<const float4 *>(wp + j * KP);
-              const float a4[4] = {av.x, av.y, av.z, av.w};
-              const float w4[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int u = 0; u < 4; ++u) acc[i][u] = fmaf(a4[i], w4[u], acc[i][u]);
+          if (out == 1) {
+            for (int e = tid; e < in * nchunk; e += NT) {
+              const int k = fdiv(e, inv_nchunk), c = e - k * nchunk;
+              const float4 dv = *reinterpret_cast<const float4 *>(DL + 4 * c);
+              const float4 hv = *reinterpret_cast<const float4 *>(Hin + k * BS + 4 * c);
+              const float w = WT[k];
+              *reinterpret_cast<float4 *>(DN + k * BS + 4 * c) =
+                  make_float4(dv.x * w * f_act_bwd(actp, hv.x), dv.y * w * f_act_bwd(actp, hv.y),
+                              dv.z * w * f_act_bwd(actp, hv.z), dv.w * w * f_act_bwd(actp, hv.w));
             }
+          } else {
+            const int ntile = nchunk * (r4(in) / 4);
+            for (int tt = tid; tt < ntile; tt += NT) {
+              const int tk = fdiv(tt, inv_nchunk), tp = tt - tk * nchunk;
+              float acc[4][4] = {};
+              tile_fma(DL + tp * 4, BS, WT + tk * 4, KP, out, acc);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int k = tk * 4 + u;
-              if (k < in) {
-                const float4 hv = *reinterpret_cast<const float4 *>(Hin + k * BS + tp * 4);
-                float4 o;
-                o.x = acc[0][u] * f_act_bwd(actp, hv.x);
-                o.y = acc[1][u] * f_act_bwd(actp, hv.y);
-                o.z = acc[2][u] * f_act_bwd(actp, hv.z);
-                o.w = acc[3][u] * f_act_bwd(actp, hv.w);
-                *reinterpret_cast<float4 *>(DN + k * BS + tp * 4) = o;
+              for (int u = 0; u < 4; ++u) {
+                const int k = tk * 4 + u;
+                if (k < in) {
+                  const float4 hv = *reinterpret_cast<const float4 *>(Hin + k * BS + tp * 4);
+                  float4 o;
+                  o.x = acc[0][u] * f_act_bwd(actp, hv.x);
+                  o.y = acc[1][u] * f_act_bwd(actp, hv.y);
+                  o.z = acc[2][u] * f_act_bwd(actp, hv.z);
+                  o.w = acc[3][u] * f_act_bwd(actp, hv.w);
+                  *reinterpret_cast<float4 *>(DN + k * BS + tp * 4) = o;
+                }
               }
             }
           }
         }
-        __syncthreads();  // delta_{l-1} done with W_l before W_l changes
-        // (2) dW_l = h_{l-1}^T delta_l (+2*l2*w), Adam in place; thread tile 4(k) x 4(j),
-        //     k strided so that consecutive lanes read consecutive activation rows
-        {
-          const float *Hin = sm + P.h[l];
+        if (ks > 0) {
+          // (2a) partial gradients of layer l over sample split s, into gs[s][psz] -- same phase as
+          //      (1): both only read.  chunks [c0, c1) of 4 samples belong to split s.
+          const int cps = (nchunk + ks - 1) >> (__ffs(ks) - 1);  // ks is a power of two
+          if (out == 1) {
+            const float inv_in1 = 1.f / (float)(in + 1);
+            for (int e = tid; e < (in + 1) * ks; e += NT) {
+              const int s = fdiv(e, inv_in1), k = e - s * (in + 1);
+              const int c0 = s * cps, c1 = min(c0 + cps, nchunk);
+              float g = 0.f;
+              for (int c = c0; c < c1; ++c) {
+                const float4 dv = *reinterpret_cast<const float4 *>(DL + 4 * c);
+                if (k < in) {
+                  const float4 hv = *reinterpret_cast<const float4 *>(Hin + k * BS + 4 * c);
+                  g = fmaf(hv.x, dv.x, g); g = fmaf(hv.y, dv.y, g);
+                  g = fmaf(hv.z, dv.z, g); g = fmaf(hv.w, dv.w, g);
+                } else {
+                  g += (dv.x + dv.y) + (dv.z + dv.w);
+                }
+              }
+              gs[s * psz + k] = g;  // k == in: the bias slot
+            }
+          } else {
+            const int tjn = JP / 4, tkn = (in + 3) / 4, ntile = tkn * tjn;
+            const float inv_ntile = 1.f / (float)ntile, inv_tjn = 1.f / (float)tjn;
+            for (int e = tid; e < ntile * ks; e += NT) {
+              const int s = fdiv(e, inv_ntile), tt = e - s * ntile;
+              const int tk = fdiv(tt, inv_tjn), tj = tt - tk * tjn;
+              // lanes walk j (rows tj, tj + tjn, ... of delta: bank-conflict-free float4 loads, and
+              // contiguous scalar stores below); the 4 k rows of a tile are adjacent
+              const int c0 = s * cps, c1 = min(c0 + cps, nchunk);
+              float acc[4][4] = {};
+              int kk[4], jj[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                kk[u] = min(tk * 4 + u, in - 1);
+                jj[u] = min(tj + u * tjn, out - 1);
+              }
+              for (int c = c0; c < c1; ++c) {
+                float4 hv[4], dv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  hv[u] = *reinterpret_cast<const float4 *>(Hin + kk[u] * BS + 4 * c);
+                  dv[u] = *reinterpret_cast<const float4 *>(DL + jj[u] * BS + 4 * c);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    acc[i][u] = fmaf(hv[i].x, dv[u].x, acc[i][u]);
+                    acc[i][u] = fmaf(hv[i].y, dv[u].y, acc[i][u]);
+                    acc[i][u] = fmaf(hv[i].z, dv[u].z, acc[i][u]);
+                    acc[i][u] = fmaf(hv[i].w, dv[u].w, acc[i][u]);
+                  }
+              }
+              float *gp_s = gs + s * psz;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int k = tk * 4 + i;
+                if (k >= in) continue;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const int j = tj + u * tjn;
+                  if (j < out) gp_s[k * out + j] = acc[i][u];
+                }
+              }
+            }
+            // bias partials: db_j over split s
+            for (int e = tid; e < out * ks; e += NT) {
+              const int s = fdiv(e, inv_out), j = e - s * out;
+              const int c0 = s * cps, c1 = min(c0 + cps, nchunk);
+              float g = 0.f;
+              for (int c = c0; c < c1; ++c) {
+                const float4 dv = *reinterpret_cast<const float4 *>(DL + j * BS + 4 * c);
+                g += (dv.x + dv.y) + (dv.z + dv.w);
+              }
+              gs[s * psz + in * out + j] = g;
+            }
+          }
+          __syncthreads();
+          // (2b) Adam on layer l, one parameter per thread in flat order (coalesced slot traffic);
+          //      four parameters' slots are requested before the first is used
+          {
+            float *W = sm + P.w[l];
+            float *WT = sm + P.wt[l];
+            float *bsm = sm + P.b[l];
+            const float l2k = a.l2k[l], l2b = a.l2b[l];
+            const int nw = in * out, g0 = d.w_off[l];
+            for (int e0 = tid; e0 < psz; e0 += 4 * NT) {
+              float mq[4], vq[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int e = e0 + q * NT;
+                if (e < psz) { mq[q] = __ldcg(gm + g0 + e); vq[q] = __ldcg(gv + g0 + e); }
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int e = e0 + q * NT;
+                if (e >= psz) continue;
+                float g = gs[e];
+                for (int s = 1; s < ks; ++s) g += gs[s * psz + e];
+                if (e < nw) {
+                  const int k = fdiv(e, inv_out), j = e - k * out;
+                  float wv = W[k * JP + j];
+                  if (l2k != 0.f) { reg += l2k * wv * wv; g += 2.f * l2k * wv; }
+                  wv = adam_update(wv, g, mq[q], vq[q], om1, om2, alpha, a.eps);
+                  W[k * JP + j] = wv;
+                  if (l > 0) WT[j * KP + k] = wv;
+                } else {
+                  const int j = e - nw;
+                  float bv = bsm[j];
+                  if (l2b != 0.f) { reg += l2b * bv * bv; g += 2.f * l2b * bv; }
+                  bsm[j] = adam_update(bv, g, mq[q], vq[q], om1, om2, alpha, a.eps);
+                }
+                gm[g0 + e] = mq[q];
+                gv[g0 + e] = vq[q];
+              }
+            }
+          }
+        } else {
+          __syncthreads();  // delta_{l-1} done with W_l before W_l changes
+          // (2') enough tiles for every thread: dW_l = h_{l-1}^T delta_l (+2*l2*w) and Adam by the
+          //      tile's owner; thread tile 4(k) x 4(j), k strided so that consecutive lanes read
+          //      consecutive activation rows
           float *W = sm + P.w[l];
           float *WT = sm + P.wt[l];
           const float l2k = a.l2k[l], l2b = a.l2b[l];
@@ -294,8 +518,7 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_kernel(const FitArgs a) {
             int kk[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) kk[u] = min(tk + u * tkn, in - 1);
-            // Adam slots of this tile: requested from L2 now, consumed after the GEMM loop, so
-            // their latency hides behind the accumulation
+            // Adam slots of this tile: requested from L2 now, consumed after the GEMM loop
             float am[4][4], av[4][4];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -335,9 +558,7 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_kernel(const FitArgs a) {
                 float g = acc[i][u];
                 if (l2k != 0.f) { reg += l2k * wv * wv; g += 2.f * l2k * wv; }
                 float m = am[i][u], v = av[i][u];
-                m += (g - m) * om1;
-                v += (g * g - v) * om2;
-                wv -= (m * alpha) / (sqrtf(v) + a.eps);
+                wv = adam_update(wv, g, m, v, om1, om2, alpha, a.eps);
                 gm[gi] = m; gv[gi] = v;
                 W[k * JP + j] = wv;
                 if (l > 0) WT[j * KP + k] = wv;
@@ -352,9 +573,7 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_kernel(const FitArgs a) {
             float bv = sm[P.b[l] + j];
             if (l2b != 0.f) { reg += l2b * bv * bv; g += 2.f * l2b * bv; }
             float m = gm[gi], v = gv[gi];
-            m += (g - m) * om1;
-            v += (g * g - v) * om2;
-            bv -= (m * alpha) / (sqrtf(v) + a.eps);
+            bv = adam_update(bv, g, m, v, om1, om2, alpha, a.eps);
             gm[gi] = m; gv[gi] = v;
             sm[P.b[l] + j] = bv;
           }
@@ -371,7 +590,7 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_kernel(const FitArgs a) {
   // ---- write the trained weights back ----
   __syncthreads();
   for (int l = 0; l < L; ++l) {
-    const int in = d.dims[l], out = d.dims[l + 1], JP = r4(out);
+    const int in = d.dims[l], out = d.dims[l + 1], JP = P.JP[l];
     for (int e = tid; e < in * out; e += NT) {
       const int k = e / out, j = e - k * out;
       gp[d.w_off[l] + e] = sm[P.w[l] + k * JP + j];
@@ -907,9 +1126,6 @@ int bore_mlp_fit(bore_mlp *h, int model0, int count, const float *X_dev, const f
   FitArgs a;
   a.d = h->desc;
   const int B = batch_size < N ? batch_size : N;
-  make_fit_plan(a.d, B, a.P);
-  const size_t smem = (size_t)a.P.total * sizeof(float);
-  BORE_CHECK(smem <= 227 * 1024, "bore_mlp_fit: model + batch of %d need %zu B of shared memory", B, smem);
   a.params = h->params; a.adam_m = h->adam_m; a.adam_v = h->adam_v; a.adam_t = h->adam_t;
   a.model0 = model0;
   a.X = X_dev; a.z = z_dev; a.N = N; a.shared_data = shared_data; a.batch = batch_size;
@@ -947,11 +1163,9 @@ int bore_mlp_fit(bore_mlp *h, int model0, int count, const float *X_dev, const f
       return 0;
     }
   }
-  BORE_CUDA(cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // threads per CTA: a step is a chain of ~16 barrier-separated phases whose length hardly depends
-  // on the thread count for small nets, so with more models than CTA slots the throughput is set
-  // by how many CTAs are resident -- smaller CTAs, more of them (BORE_FIT_THREADS overrides)
-  // measured, cfg 4 (4,096 x Dense32x2 models, ms per BO iteration of all of them):
+  // threads per CTA: with more models than CTA slots the throughput is set by how many CTAs are
+  // resident -- smaller CTAs, more of them (BORE_FIT_THREADS overrides).  Measured with the first
+  // version of the kernel, cfg 4 (4,096 x Dense32x2 models, ms per BO iteration of all of them):
   // 256 threads 462, 128 threads 314, 64 threads 332, 32 threads 397
   int threads = count >= 2 * h->sm_count ? 128 : FIT_THREADS;
   {
@@ -962,6 +1176,10 @@ int bore_mlp_fit(bore_mlp *h, int model0, int count, const float *X_dev, const f
     }
     if (forced == 32 || forced == 64 || forced == 128 || forced == 256) threads = forced;
   }
+  make_fit_plan(a.d, B, threads, 226 * 1024 / (int)sizeof(float), a.P);
+  const size_t smem = (size_t)a.P.total * sizeof(float);
+  BORE_CHECK(smem <= 227 * 1024, "bore_mlp_fit: model + batch of %d need %zu B of shared memory", B, smem);
+  BORE_CUDA(cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   fit_kernel<<<count, threads, smem, (cudaStream_t)stream>>>(a);
   BORE_CUDA(cudaGetLastError());
   return 0;

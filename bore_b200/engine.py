@@ -512,8 +512,8 @@ class SvgdStepper:
 
     def step(self, f, f_grad):
         torch = _torch()
-        f = np.ascontiguousarray(np.broadcast_to(f, (self.n,)), np.float64)
-        g = np.ascontiguousarray(f_grad, np.float64)
+        f = np.array(np.broadcast_to(f, (self.n,)), np.float64)
+        g = np.array(f_grad, np.float64)
         assert g.shape == (self.n, self.D)
         f_dev, g_dev = torch.from_numpy(f).to(self._tdev), torch.from_numpy(g).to(self._tdev)
         ls, step, alpha, eps, tau, lambd, zc = self._opts
