@@ -35,6 +35,9 @@ CASES = [
     ("cfg5_plugin8", 333, 20, 64, [1e-3] * 6 + [0.0, 0.0]),  # plugin: hidden layers only
     ("cfg2_hartmann6", 128, 10, 32, 0.0),   # exact multiple, other batch size
     ("cfg2_hartmann6", 65, 10, 64, 0.0),    # last batch of ONE sample
+    ("tanh_exp", 200, 12, 50, 0.0),         # widths 24 / 40 (not multiples of 32), batch not a multiple of 4
+    ("no_hidden", 90, 15, 32, 1e-3),        # logistic regression: the 1-unit layer is the only layer
+    ("ref_test_linear", 150, 10, 64, 0.0),  # bore/models.py quirk net (3 linear hidden layers)
 ]
 
 
@@ -115,3 +118,31 @@ def test_many_models_one_launch():
         w_ref = [w.copy() for w in ws[i]]
         h_ref, _ = km.fit(w_ref, acts, *probs[i][:2], E, 64, probs[i][2])
         assert np.abs(loss[i] - h_ref).max() <= LOSS_TOL
+
+
+def test_more_models_than_cta_slots_use_small_ctas():
+    """>= 2 x 148 models switch the one-CTA kernel to 128 threads (other sample splits of the
+    gradient tiles than the 256-thread form): every problem still follows the oracle."""
+    from bore_b200.engine import NativeMLP
+    dims, acts, _ = NETS["cfg2_hartmann6"]
+    M, N, E = 300, 100, 6
+    rs = np.random.RandomState(0)
+    X = rs.uniform(size=(M, N, dims[0]))
+    y = np.stack([synthetic_targets(x) for x in X])
+    z = np.stack([row < np.quantile(row, 0.25) for row in y])
+    perms = np.stack([rs.permutation(N) for _ in range(E)])
+    ws = [km.init_weights(dims, 100 + i) for i in range(M)]
+    net = NativeMLP(dims, acts, n_models=M)
+    for i, w in enumerate(ws):
+        net.set_weights(w, model=i)
+    loss = net.fit_dev(net.to_device(X.reshape(M * N, -1), np.float32),
+                       net.to_device(z.reshape(-1).astype(np.float32), np.float32), N, 64, E,
+                       net.to_device(perms.astype(np.int32), np.int32), model0=0, count=M,
+                       shared_data=False, shared_perm=True).cpu().numpy()
+    assert loss.shape == (M, E) and np.isfinite(loss).all()
+    for i in (0, 1, 149, 298, 299):
+        w_ref = [w.copy() for w in ws[i]]
+        h_ref, _ = km.fit(w_ref, acts, X[i], z[i], E, 64, perms)
+        assert np.abs(loss[i] - h_ref).max() <= LOSS_TOL
+        for u, v in zip(net.get_weights(model=i), w_ref):
+            assert np.abs(u - v).max() <= 2e-3
