@@ -110,7 +110,7 @@ class BatchedMaximizableSequential:
         net = self._net
         loss = net.fit_dev(net.to_device(X.reshape(M * N, D), np.float32),
                            z_dev if z_dev is not None else
-                           net.to_device(z.reshape(-1).astype(np.float32), np.float32),
+                           net.to_device(z.reshape(-1), np.float32),
                            N, int(batch_size), int(epochs), net.to_device(perm, np.int32),
                            model0=0, count=M, shared_data=False, shared_perm=shared_perm)
         out = loss.cpu().numpy()

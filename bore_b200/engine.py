@@ -105,23 +105,27 @@ class NativeMLP:
     def to_device(self, a, dtype):
         """numpy -> device tensor through a cached pinned staging buffer (page-locking a fresh
         buffer per call costs more than the copy itself).  A buffer is reused once the event
-        recorded behind its last host-to-device copy has completed."""
+        recorded behind its last host-to-device copy has completed.  A dtype change (the float64
+        arrays of the reference's surface -> the kernels' float32) happens in the same pass that
+        fills the staging buffer, not in a temporary of its own."""
         torch = _torch()
-        a = np.ascontiguousarray(a, dtype=dtype)
-        tdt = torch.from_numpy(a[:0].reshape(-1)).dtype
-        if a.nbytes == 0:
+        a = np.asarray(a)
+        dtype = np.dtype(dtype)
+        tdt = torch.from_numpy(np.empty(0, dtype)).dtype
+        nbytes = a.size * dtype.itemsize
+        if nbytes == 0:
             return torch.empty(a.shape, dtype=tdt, device=self._tdev())
         pool = self.__dict__.setdefault("_pinned", [])
         best = None
         for ent in pool:
-            if ent[0].numel() >= a.nbytes and ent[1].query() and (best is None or ent[0].numel() < best[0].numel()):
+            if ent[0].numel() >= nbytes and ent[1].query() and (best is None or ent[0].numel() < best[0].numel()):
                 best = ent
         if best is None:
-            cap = 1 << max(12, int(a.nbytes - 1).bit_length())
+            cap = 1 << max(12, int(nbytes - 1).bit_length())
             try:
                 buf = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
             except RuntimeError:
-                return torch.from_numpy(a).to(self._tdev())
+                return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).to(self._tdev())
             best = [buf, torch.cuda.Event()]
             pool.append(best)
             if len(pool) > 16:  # drop the oldest idle buffer
@@ -129,8 +133,8 @@ class NativeMLP:
                     if ent[1].query():
                         del pool[i]
                         break
-        view = best[0][:a.nbytes].view(tdt).reshape(a.shape)
-        view.numpy()[...] = a
+        view = best[0][:nbytes].view(tdt).reshape(a.shape)
+        np.copyto(view.numpy(), a, casting="unsafe")
         out = view.to(self._tdev(), non_blocking=True)
         best[1].record(torch.cuda.current_stream(self.device))
         return out
