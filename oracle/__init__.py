@@ -18,4 +18,8 @@ Parity status
   gradient are cross-checked against torch-CPU autograd (tests/test_oracle.py).
 * Host helpers (math.py, optimizers/utils.py, data.py): pinned against the reference
   modules themselves, which import fine here (tests/golden/make_golden.py).
+* Data step (data_step.py) and SVGD batch argmax (svgd.py): **pinned** -- bore.data and
+  bore.optimizers.svgd import here (numpy / scipy / sklearn only); the fixtures
+  tests/golden/{data_step,svgd}_golden.npz are outputs of the reference code itself and the
+  restatements reproduce them exactly.
 """
