@@ -633,9 +633,12 @@ struct FitCPlan {
   int total, SP, chunk, wend;  // wend: end of the weight images (offsets must fit 16 bits)
 };
 
-// leading dimensions of the weight images: odd, so that lanes reading one column at different
-// rows (the k-split of dense_pass) hit different banks
-__host__ __device__ inline int ldo(int n) { return r4(n) + 1; }
+// leading dimension of the weight images: = 8 (mod 32).  In dense_pass a warp reads W[k][j] for
+// 4 interleaved k (the k-split of an output over adjacent lanes) x 8 adjacent j: with this stride
+// the 32 addresses fall into 32 different banks (an odd stride, the first choice, separated the k
+// rows of ONE column but let (k, j) and (k+1, j-1) collide: half of all shared-memory wavefronts
+// of the kernel were bank conflicts, profiles/r01_ncu_fit_cluster_v5.txt)
+__host__ __device__ inline int ldo(int n) { return n <= 8 ? 8 : ((n - 8 + 31) / 32) * 32 + 8; }
 
 __host__ __device__ inline void make_fitc_plan(const MlpDesc &d, int batch, FitCPlan &p) {
   const int L = d.n_layers;
@@ -845,6 +848,7 @@ fit_cluster_kernel(const FitCArgs a) {
   }
   if (tid < 4) sm[P.slots + tid] = 0.f;
   long long t_step = a.adam_t[model];
+  double b1p_d = pow((double)a.beta1, (double)t_step), b2p_d = pow((double)a.beta2, (double)t_step);
   uint32_t peer[FIT_CLUSTER];  // base of every CTA's dynamic shared memory
 #pragma unroll
   for (int c = 0; c < FIT_CLUSTER; ++c) peer[c] = dsmem_addr(sm, c);
@@ -900,7 +904,9 @@ fit_cluster_kernel(const FitCArgs a) {
 
       // ---- Adam scalars for this step (Keras: t starts at 1) ----
       t_step += 1;
-      const float b1p = powf(a.beta1, (float)t_step), b2p = powf(a.beta2, (float)t_step);
+      b1p_d *= (double)a.beta1;
+      b2p_d *= (double)a.beta2;
+      const float b1p = (float)b1p_d, b2p = (float)b2p_d;
       const float alpha = a.lr * sqrtf(1.f - b2p) / (1.f - b1p);
       const float om1 = 1.f - a.beta1, om2 = 1.f - a.beta2;
 
@@ -924,17 +930,18 @@ fit_cluster_kernel(const FitCArgs a) {
           });
         }
         {
-          // partial dW_l = h_{l-1}^T delta_l over this CTA's samples: 4(k) x 4(j) register tiles
+          // partial dW_l = h_{l-1}^T delta_l over this CTA's samples: 4(k) x 4(j) register tiles;
+          // lanes walk j (rows tj, tj + tjn, ... of delta), so the stores below are contiguous
           float *dW = sm + P.dwp + d.w_off[l];
           const int tkn = (in + 3) / 4, tjn = (out + 3) / 4;
           for (int tt = tid; tt < tkn * tjn; tt += NT) {
-            const int tk = tt % tkn, tj = tt / tkn;
+            const int tj = tt % tjn, tk = tt / tjn;
             float acc[4][4] = {};
             int kk[4], jj[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              kk[u] = min(tk + u * tkn, in - 1);
-              jj[u] = min(tj * 4 + u, out - 1);
+              kk[u] = min(tk * 4 + u, in - 1);
+              jj[u] = min(tj + u * tjn, out - 1);
             }
             for (int p = 0; p < SP; p += 4) {
               float4 hv[4], dv[4];
@@ -955,11 +962,11 @@ fit_cluster_kernel(const FitCArgs a) {
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const int k = tk + i * tkn;
+              const int k = tk * 4 + i;
               if (k >= in) continue;
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
-                const int j = tj * 4 + u;
+                const int j = tj + u * tjn;
                 if (j < out) dW[k * out + j] = acc[i][u];
               }
             }
@@ -994,15 +1001,16 @@ fit_cluster_kernel(const FitCArgs a) {
           const int i = i0 + i4 + e;
           outv[e] = 0.f;
           if (i < i1) {
-            int off_w, off_wt;
-            float l2;
-            locate(i, off_w, off_wt, l2);
+            const int off_w = tab[i] & 0xffff;
             float wv = sm[off_w], g = gs[e];
-            if (l2 != 0.f) { reg += l2 * wv * wv; g += 2.f * l2 * wv; }
+            if (a.any_l2) {
+              int off_w2, off_wt2;
+              float l2;
+              locate(i, off_w2, off_wt2, l2);
+              if (l2 != 0.f) { reg += l2 * wv * wv; g += 2.f * l2 * wv; }
+            }
             float m = sm[P.am + i4 + e], v = sm[P.av + i4 + e];
-            m += (g - m) * om1;
-            v += (g * g - v) * om2;
-            wv -= (m * alpha) / (sqrtf(v) + a.eps);
+            wv = adam_update(wv, g, m, v, om1, om2, alpha, a.eps);
             sm[P.am + i4 + e] = m;
             sm[P.av + i4 + e] = v;
             outv[e] = wv;
