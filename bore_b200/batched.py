@@ -25,6 +25,39 @@ def problem_shard(n_problems, rank, world):
     return shard_bounds(n_problems, rank, world)
 
 
+class LazyLoss:
+    """The (M, epochs) epoch losses of a batched ``fit``, fetched from the device the first time
+    they are looked at: the training kernel is launched asynchronously, so the host is free to
+    stage the next ``argmax``'s screening samples while the GPU trains (the single-model
+    ``History`` of ``models.py`` does the same).  Behaves like the ndarray it wraps."""
+
+    def __init__(self, loss_dev):
+        self._dev, self._host = loss_dev, None
+        self.shape = tuple(loss_dev.shape)
+
+    def numpy(self):
+        if self._host is None:
+            self._host = self._dev.cpu().numpy()
+            self._dev = None
+        return self._host
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.numpy()
+        return a if dtype is None else a.astype(dtype)
+
+    def __getitem__(self, idx):
+        return self.numpy()[idx]
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __iter__(self):
+        return iter(self.numpy())
+
+    def __repr__(self):
+        return repr(self.numpy())
+
+
 class BatchedMaximizableSequential:
 
     def __init__(self, layers, n_problems, transform=ops.identity, seed=None, device=None):
@@ -87,7 +120,8 @@ class BatchedMaximizableSequential:
         launch.  ``permutations``: (epochs, N) shared by all problems or (M, epochs, N).
         With ``gamma`` given, ``y`` holds the RAW targets and every problem is labelled
         ``z = y < quantile(y, gamma)`` on the device (bore/data.py:31-35) before training.
-        Returns the per-problem history loss, shape (M, epochs)."""
+        Returns the per-problem history loss, shape (M, epochs), as a ``LazyLoss`` (array-like;
+        the launch is asynchronous and the values are fetched on first use)."""
         if not self._compiled:
             raise RuntimeError("You must compile your model before training/testing.")
         X = np.asarray(x)
@@ -113,7 +147,7 @@ class BatchedMaximizableSequential:
                            net.to_device(z.reshape(-1), np.float32),
                            N, int(batch_size), int(epochs), net.to_device(perm, np.int32),
                            model0=0, count=M, shared_data=False, shared_perm=shared_perm)
-        out = loss.cpu().numpy()
+        out = LazyLoss(loss)
         if verbose:
             print(f"fit: {M} problems x {epochs} epochs, mean loss {out[:, 0].mean():.4f} -> "
                   f"{out[:, -1].mean():.4f}")

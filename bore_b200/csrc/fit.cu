@@ -439,14 +439,22 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_kernel(const FitArgs a) {
                   }
               }
               float *gp_s = gs + s * psz;
+              if (((in | out) & 3) == 0) {  // whole tiles: no predicates, one base address
+                float *dp = gp_s + tk * 4 * out + tj;
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int k = tk * 4 + i;
-                if (k >= in) continue;
+                for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const int j = tj + u * tjn;
-                  if (j < out) gp_s[k * out + j] = acc[i][u];
+                  for (int u = 0; u < 4; ++u) dp[i * out + u * tjn] = acc[i][u];
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int k = tk * 4 + i;
+                  if (k >= in) continue;
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const int j = tj + u * tjn;
+                    if (j < out) gp_s[k * out + j] = acc[i][u];
+                  }
                 }
               }
             }
@@ -464,42 +472,52 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_kernel(const FitArgs a) {
           }
           __syncthreads();
           // (2b) Adam on layer l, one parameter per thread in flat order (coalesced slot traffic);
-          //      four parameters' slots are requested before the first is used
+          //      four parameters' slots are requested before the first is used.  Weights first,
+          //      then the biases (no per-element branch between the two kinds).
           {
             float *W = sm + P.w[l];
             float *WT = sm + P.wt[l];
             float *bsm = sm + P.b[l];
             const float l2k = a.l2k[l], l2b = a.l2b[l];
             const int nw = in * out, g0 = d.w_off[l];
-            for (int e0 = tid; e0 < psz; e0 += 4 * NT) {
+            auto grad_sum = [&](int e) {
+              float g = gs[e];
+              if (ks == 2) return g + gs[psz + e];
+              for (int s = 1; s < ks; ++s) g += gs[s * psz + e];
+              return g;
+            };
+            for (int e0 = tid; e0 < nw; e0 += 4 * NT) {
               float mq[4], vq[4];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const int e = e0 + q * NT;
-                if (e < psz) { mq[q] = __ldcg(gm + g0 + e); vq[q] = __ldcg(gv + g0 + e); }
+                const int e = min(e0 + q * NT, nw - 1);
+                mq[q] = __ldcg(gm + g0 + e);
+                vq[q] = __ldcg(gv + g0 + e);
               }
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const int e = e0 + q * NT;
-                if (e >= psz) continue;
-                float g = gs[e];
-                for (int s = 1; s < ks; ++s) g += gs[s * psz + e];
-                if (e < nw) {
-                  const int k = fdiv(e, inv_out), j = e - k * out;
-                  float wv = W[k * JP + j];
-                  if (l2k != 0.f) { reg += l2k * wv * wv; g += 2.f * l2k * wv; }
-                  wv = adam_update(wv, g, mq[q], vq[q], om1, om2, alpha, a.eps);
-                  W[k * JP + j] = wv;
-                  if (l > 0) WT[j * KP + k] = wv;
-                } else {
-                  const int j = e - nw;
-                  float bv = bsm[j];
-                  if (l2b != 0.f) { reg += l2b * bv * bv; g += 2.f * l2b * bv; }
-                  bsm[j] = adam_update(bv, g, mq[q], vq[q], om1, om2, alpha, a.eps);
-                }
+                if (e >= nw) break;
+                float g = grad_sum(e);
+                const int k = fdiv(e, inv_out), j = e - k * out;
+                float wv = W[k * JP + j];
+                if (l2k != 0.f) { reg += l2k * wv * wv; g += 2.f * l2k * wv; }
+                wv = adam_update(wv, g, mq[q], vq[q], om1, om2, alpha, a.eps);
+                W[k * JP + j] = wv;
+                if (l > 0) WT[j * KP + k] = wv;
                 gm[g0 + e] = mq[q];
                 gv[g0 + e] = vq[q];
               }
+            }
+            for (int j = tid; j < out; j += NT) {
+              const int e = nw + j;
+              float g = grad_sum(e);
+              float bv = bsm[j];
+              if (l2b != 0.f) { reg += l2b * bv * bv; g += 2.f * l2b * bv; }
+              float m = __ldcg(gm + g0 + e), v = __ldcg(gv + g0 + e);
+              bsm[j] = adam_update(bv, g, m, v, om1, om2, alpha, a.eps);
+              gm[g0 + e] = m;
+              gv[g0 + e] = v;
             }
           }
         } else {

@@ -118,7 +118,11 @@ class NativeMLP:
         pool = self.__dict__.setdefault("_pinned", [])
         best = None
         for ent in pool:
-            if ent[0].numel() >= nbytes and ent[1].query() and (best is None or ent[0].numel() < best[0].numel()):
+            # a buffer serves payloads of its own size class only (>= a quarter of its capacity):
+            # a small upload must not occupy the staging buffer of a large one, whose next use
+            # would then have to page-lock a fresh buffer (~100 ms for 256 MB)
+            if (ent[0].numel() >= nbytes and ent[0].numel() <= max(4 * nbytes, 1 << 16) and ent[1].query()
+                    and (best is None or ent[0].numel() < best[0].numel())):
                 best = ent
         if best is None:
             cap = 1 << max(12, int(nbytes - 1).bit_length())
