@@ -738,50 +738,83 @@ LB_FN int lb_formk(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
   const double theta = s.theta;
   LB_SYNC();
 #if LB_WARP
+  // Gram matrix of the compacted columns V = [Y(:, 0..col) S(:, 0..col)] over the SMALLER of
+  // the free / active index sets (the other set follows from the kept totals SY, SS, YY), on the
+  // FP64 tensor cores: G = V'V as 8x8 tiles of mma.sync.m8n8k4 (DMMA), four selected rows of W per
+  // step.  For tile T a lane holds V[k0 + lane%4][8T + lane/4], which is the A fragment of tile
+  // row T and the B fragment of tile column T alike, so three shared-memory loads feed the six
+  // tiles of the upper triangle.  Entry (r, c), r <= c, of G belongs at wn[r][c] -- the position
+  // of the same entry of the 2col x 2col middle matrix -- after the family's affine map:
+  //   r, c <  col : Y'ZZ'Y / theta + D            (j = r, i = c)
+  //   r, c >= col : theta * S'AA'S                (j = r - col, i = c - col)
+  //   r < col <= c: L_a' / R_z' (sy - g or g, sign by j >= i; y index j = r, s index i = c - col)
+  // (The first device version gave every lane 7 of the 210 outputs and walked the rows with two
+  // loads and a DFMA per output and row: 15 % of the stepper's instructions.)
   const LbDP W = w.W;
   const bool over_free = nfree <= n - nfree;
   const LbIP ind = over_free ? w.index : w.index + nfree;
   const int nq = over_free ? nfree : n - nfree;
-  const int nout = m * (m + 1) + m * m;
-  double acc[LB_FORMK_ACC];
-  int code[LB_FORMK_ACC];
+  const int twoc = 2 * col;
+  const int kq = LB_LANE & 3, rq = LB_LANE >> 2;
+  int coff[3];
 #pragma unroll
-  for (int t = 0; t < LB_FORMK_ACC; ++t) {
-    acc[t] = 0.0;
-    code[t] = w.ftab[LB_LANE + 32 * t];
+  for (int T = 0; T < 3; ++T) {
+    const int r = 8 * T + rq;
+    coff[T] = r >= twoc ? -1 : (r < col ? r : m + (r - col));
   }
-  LB_UNROLL_HOT2
-  for (int k = 0; k < nq; ++k) {
-    const LbDP row = W + ind[k] * ldw;
+  double acc[12];
 #pragma unroll
-    for (int t = 0; t < LB_FORMK_ACC; ++t)
-      acc[t] += row[(code[t] >> 14) & 255] * row[(code[t] >> 22) & 255];
-  }
-  // write-out as a ROLLED loop (one copy of the code instead of seven): the accumulators take
-  // a detour through a dynamically indexed (local-memory) array
-  double accm[LB_FORMK_ACC];
-#pragma unroll
-  for (int t = 0; t < LB_FORMK_ACC; ++t) accm[t] = acc[t];
+  for (int t = 0; t < 12; ++t) acc[t] = 0.0;
+#define LB_DMMA(t, a, b)                                                                          \
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"   \
+               : "+d"(acc[2 * (t)]), "+d"(acc[2 * (t) + 1]) : "d"(a), "d"(b))
   LB_UNROLL1
-  for (int t = 0; t < LB_FORMK_ACC; ++t) {
-    const int o = LB_LANE + 32 * t;
-    if (o >= nout) break;
-    const int cd = w.ftab[o];
-    const int ty = cd & 3, i = (cd >> 2) & 63, j = (cd >> 8) & 63;
-    if (i >= col || j >= col) continue;
-    const double g = accm[t];
-    if (ty == 0) {         // Y'ZZ'Y/theta + D at (j, i), i >= j
-      double a = over_free ? g : w.yy[i * m + j] - g;
-      a /= theta;
-      if (i == j) a += w.sy[i * m + i];
-      w.wn[j * ldn + i] = a;
-    } else if (ty == 1) {  // theta * S'AA'S at (col+j, col+i), i >= j
-      const double a = over_free ? w.ss[i * m + j] - g : g;
-      w.wn[(col + j) * ldn + (col + i)] = a * theta;
-    } else {               // ws column i with wy column j, at (j, col+i)
-      if (j >= i) w.wn[j * ldn + (col + i)] = over_free ? g : w.sy[i * m + j] - g;
-      else w.wn[j * ldn + (col + i)] = -(over_free ? w.sy[i * m + j] - g : g);
+  for (int k0 = 0; k0 < nq; k0 += 4) {
+    const int kk = k0 + kq;
+    const bool kv = kk < nq;
+    const LbDP row = W + (kv ? ind[kk] : 0) * ldw;
+    const double v0 = (kv && coff[0] >= 0) ? row[coff[0] < 0 ? 0 : coff[0]] : 0.0;
+    const double v1 = (kv && coff[1] >= 0) ? row[coff[1] < 0 ? 0 : coff[1]] : 0.0;
+    const double v2 = (kv && coff[2] >= 0) ? row[coff[2] < 0 ? 0 : coff[2]] : 0.0;
+    LB_DMMA(0, v0, v0);
+    if (twoc > 8) {
+      LB_DMMA(1, v0, v1);
+      LB_DMMA(3, v1, v1);
     }
+    if (twoc > 16) {
+      LB_DMMA(2, v0, v2);
+      LB_DMMA(4, v1, v2);
+      LB_DMMA(5, v2, v2);
+    }
+  }
+#undef LB_DMMA
+  // write-out as a ROLLED loop (one copy of the code): the accumulators take a detour through
+  // a dynamically indexed (local-memory) array.  Tile t = (R, C) of the upper triangle:
+  // (0,0) (0,1) (0,2) (1,1) (1,2) (2,2); a lane holds (8R + lane/4, 8C + 2 (lane%4) + {0, 1}).
+  double accm[12];
+#pragma unroll
+  for (int t = 0; t < 12; ++t) accm[t] = acc[t];
+  LB_UNROLL1
+  for (int q = 0; q < 12; ++q) {
+    const int t = q >> 1;
+    const int r = 8 * ((0x211000 >> (4 * t)) & 15) + rq;
+    const int c = 8 * ((0x221210 >> (4 * t)) & 15) + 2 * kq + (q & 1);
+    if (r > c || c >= twoc) continue;
+    const double g = accm[q];
+    double a;
+    if (c < col) {          // Y'ZZ'Y / theta + D
+      a = over_free ? g : w.yy[c * m + r] - g;
+      a /= theta;
+      if (r == c) a += w.sy[c * m + c];
+    } else if (r >= col) {  // theta * S'AA'S
+      const int i = c - col, j = r - col;
+      a = (over_free ? w.ss[i * m + j] - g : g) * theta;
+    } else {                // s column i with y column j
+      const int i = c - col, j = r;
+      if (j >= i) a = over_free ? g : w.sy[i * m + j] - g;
+      else a = -(over_free ? w.sy[i * m + j] - g : g);
+    }
+    w.wn[r * ldn + c] = a;
   }
 #else
   (void)nfree; (void)n; (void)ldw;
