@@ -181,8 +181,20 @@ LB_FN void lb_carve(LbWork &w, double *dbase, int *ibase, int n, int m) {
 // 0 ok, else k+1.  Right-looking: after column k is scaled, lane j owns column k+1+j of the
 // trailing block and walks its rows, so there is no index arithmetic in the inner loop.
 #if LB_WARP
-// 1/sqrt(a); one copy of the (long) fp64 sequence for the unrolled caller
-LB_NI double lb_rsqrt(double a) { return rsqrt(a); }
+// 1/sqrt(a) for a Cholesky pivot a > 0 (checked by the caller, normal range): the hardware seed
+// rsqrt.approx.ftz.f64 (relative error 2^-22) and two Newton steps y += y (1/2 - (a/2) y^2), i.e.
+// 2^-43, then fp64 rounding level -- 9 instructions.  CUDA's rsqrt() spends ~35 on the same
+// value plus the special cases (zero, denormal, inf, NaN) that cannot occur here; 30 pivots per
+// iteration made it 4 % of the stepper's instructions (profiles/r01_notes.md).
+__device__ __forceinline__ double lb_rsqrt(double a) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  const double h = 0.5 * a;
+  double e = fma(-h, y * y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-h, y * y, 0.5);
+  return fma(y, e, y);
+}
 #endif
 LB_NI int lb_chol(double *A, int ld, int n, double *rd) {
   LB_SHARED(A); LB_SHARED(rd);
