@@ -39,11 +39,37 @@
 #include "common.cuh"
 #include "lbfgsb_types.h"
 
-namespace lbw {  // warp-collective variant
+namespace lbw {  // warp-collective variant, run-time history size m
 #define LB_VARIANT 1
 #include "lbfgsb_core.h"
 #undef LB_VARIANT
 }  // namespace lbw
+namespace lbw10 {  // the same with m = 10 (SciPy's default maxcor) as a compile-time constant
+#define LB_VARIANT 1
+#define LB_MCONST 10
+#include "lbfgsb_core.h"
+#undef LB_MCONST
+#undef LB_VARIANT
+}  // namespace lbw10
+
+// the two compilations of the core behind one name
+template <int MC> struct LbCore;
+template <> struct LbCore<0> {
+  using Work = lbw::LbWork;
+  static __device__ __forceinline__ void carve(Work &w, double *d, int *i, int n, int m) { lbw::lb_carve(w, d, i, n, m); }
+  template <class Mem>
+  static __device__ __forceinline__ int advance(const LbParams &P, Work &w, LbScal &s, Mem &mem, int stage) {
+    return lbw::lb_advance(P, w, s, mem, stage);
+  }
+};
+template <> struct LbCore<10> {
+  using Work = lbw10::LbWork;
+  static __device__ __forceinline__ void carve(Work &w, double *d, int *i, int n, int m) { lbw10::lb_carve(w, d, i, n, m); }
+  template <class Mem>
+  static __device__ __forceinline__ int advance(const LbParams &P, Work &w, LbScal &s, Mem &mem, int stage) {
+    return lbw10::lb_advance(P, w, s, mem, stage);
+  }
+};
 namespace {
 
 constexpr int SCAL_BYTES = LB_SCAL_DOUBLES * sizeof(double);
@@ -240,7 +266,7 @@ __host__ __device__ inline size_t lb_header_bytes(int n, int wpb) {
 // stage (memory update, Cauchy point, K factorisation, subspace minimisation) phase by phase
 // between CTA barriers -- ~10^4 instructions that the warps now fetch together instead of each
 // thrashing the instruction caches from a different place (profiles/r01_notes.md).
-template <typename FG>
+template <typename FG, int MC>
 __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t warp_bytes, int nphase) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int n = D.P.n, m = D.P.m;
@@ -295,9 +321,9 @@ __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t w
   LbParams P = D.P;
   P.lo = s_lo; P.hi = s_hi; P.nbd = s_nbd;
 
-  lbw::LbWork w;
-  lbw::lb_carve(w, reinterpret_cast<double *>(base),
-                reinterpret_cast<int *>(base + lbw::lb_work_doubles(n, m) * sizeof(double)), n, m);
+  typename LbCore<MC>::Work w;
+  LbCore<MC>::carve(w, reinterpret_cast<double *>(base),
+                    reinterpret_cast<int *>(base + lbw::lb_work_doubles(n, m) * sizeof(double)), n, m);
   w.ftab = ftab;
   LbScal *s_smem = reinterpret_cast<LbScal *>(base);
   const FG *F = static_cast<const FG *>(D.F);
@@ -388,20 +414,20 @@ __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t w
       mem.cap = nphase < 0 ? 0 : nphase;
       col_in = s.col;
       was_ls = s.phase == LB_PH_LNSRCH;
-      const int r = lbw::lb_advance(P, w, s, mem, 1);
+      const int r = LbCore<MC>::advance(P, w, s, mem, 1);
       if (r == 2) { holding = true; break; }
       finish(r);
     }
     if (nphase < 0) {  // free-running warps (no alignment at all): tuning / comparison mode
       if (!holding) break;
-      const int r = lbw::lb_advance(P, w, s, mem, 2);
+      const int r = LbCore<MC>::advance(P, w, s, mem, 2);
       finish(r);
       continue;
     }
     if (!__syncthreads_or(holding ? 1 : 0)) break;
     // ---- heavy stage, phase-aligned across the CTA ----
     if (holding) {
-      const int r = lbw::lb_advance(P, w, s, mem, 2);
+      const int r = LbCore<MC>::advance(P, w, s, mem, 2);
 #pragma unroll 1
       while (mem.nph < nphase) { __syncthreads(); ++mem.nph; }
       finish(r);
@@ -528,15 +554,21 @@ int setup_params(LbDev &D, const LbLayout &L, char *work, int S, int n, int m, c
 }
 
 // one round of the stepper
+template <typename FG, int MC>
+int launch_round_mc(const LbDev &D, const StepLaunch &SL, int round, int nphase, cudaStream_t stream) {
+  static bool attr_done = false;  // one flag per instantiation
+  if (!attr_done) {  // opt in to > 48 KB of dynamic shared memory (once per kernel)
+    BORE_CUDA(cudaFuncSetAttribute(lbfgsb_warp_kernel<FG, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   227 * 1024));
+    attr_done = true;
+  }
+  lbfgsb_warp_kernel<FG, MC><<<SL.grid, SL.block, SL.smem, stream>>>(D, round, SL.warp_bytes, nphase);
+  return 0;
+}
+
+// one round of the stepper
 template <typename FG>
 int launch_round(const LbDev &D, const StepLaunch &SL, int round, cudaStream_t stream) {
-  static bool attr_done[2] = {false, false};
-  const int which = sizeof(FG) == 8;
-  if (!attr_done[which]) {  // opt in to > 48 KB of dynamic shared memory (once per kernel)
-    BORE_CUDA(cudaFuncSetAttribute(lbfgsb_warp_kernel<FG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   227 * 1024));
-    attr_done[which] = true;
-  }
   static int nphase = -1;
   if (nphase < 0) {
     const char *e = getenv("BORE_LB_NPHASE");
@@ -544,8 +576,8 @@ int launch_round(const LbDev &D, const StepLaunch &SL, int round, cudaStream_t s
     if (nphase < -1) nphase = -1;
     if (nphase > LB_NPHASE_MAX) nphase = LB_NPHASE_MAX;
   }
-  lbfgsb_warp_kernel<FG><<<SL.grid, SL.block, SL.smem, stream>>>(D, round, SL.warp_bytes, nphase);
-  return 0;
+  if (D.P.m == 10) return launch_round_mc<FG, 10>(D, SL, round, nphase, stream);
+  return launch_round_mc<FG, 0>(D, SL, round, nphase, stream);
 }
 
 // header kept at the very start of the external-API workspace so step/results can find things

@@ -33,6 +33,7 @@
 #endif
 
 #undef LB_FN
+#undef LB_M
 #undef LB_WARP
 #undef LB_LANE
 #undef LB_NL
@@ -80,6 +81,17 @@
 #define LB_SYNC() ((void)0)
 #endif
 #define LB_FOR(i, n) LB_UNROLL1 for (int i = LB_LANE; i < (n); i += LB_NL)
+
+// The history size m (SciPy's `maxcor`).  The includer may define LB_MCONST: the device build
+// is compiled a second time with m = 10 (the default, which the reference never changes) as a
+// compile-time constant, so that the i*m + k / k*ldn + ... index arithmetic of every small dense
+// kernel below folds into shifts and immediates (IMAD + IMAD.IADD were 13 % of the stepper's
+// instructions with a run-time m).
+#ifdef LB_MCONST
+#define LB_M(x) (LB_MCONST)
+#else
+#define LB_M(x) (x)
+#endif
 
 typedef double *LbDP;
 typedef int *LbIP;
@@ -160,6 +172,7 @@ LB_HD size_t lb_work_doubles(int n, int m) {
 LB_HD size_t lb_work_ints(int n) { return 2 * (size_t)n; }
 
 LB_FN void lb_carve(LbWork &w, double *dbase, int *ibase, int n, int m) {
+  m = LB_M(m);
   // persisted block first (see LB_PERSIST_DOUBLES), scratch after it
   const int nv = LB_NV(n);
   double *q = dbase + LB_SCAL_DOUBLES;
@@ -314,6 +327,7 @@ LB_NI void lb_trsl_n(const double *R, int ld, int n, const double *rd, double *b
 
 // ld = L D^-1 below the diagonal, 1/D on it (L, D = strictly lower part / diagonal of SY)
 LB_FN void lb_prep_ld(LbWork &w, int m, int col) {
+  m = LB_M(m);
   LB_SYNC();
   LB_FOR(k, col) w.ld[k * m + k] = 1.0 / w.sy[k * m + k];
   LB_SYNC();
@@ -334,6 +348,7 @@ LB_FN void lb_prep_ld(LbWork &w, int m, int col) {
 // through the precomputed operators tinv and ld (see LbWork).  v and p must not alias.
 LB_NI void lb_bmv(const double *ld, const double *tinv, double *q, int m, int col,
                   const double *v, double *p) {
+  m = LB_M(m);
   LB_SHARED(ld); LB_SHARED(tinv); LB_SHARED(q); LB_SHARED(v); LB_SHARED(p);
   if (col == 0) return;
   LB_SYNC();
@@ -364,6 +379,7 @@ LB_NI void lb_bmv(const double *ld, const double *tinv, double *q, int m, int co
 // w.tinv: every later bmv is a plain matrix-vector product.  Returns nonzero when T is not
 // positive definite (the caller refreshes the memory, like the original).
 LB_FN int lb_formt(LbWork &w, int m, int col, double theta) {
+  m = LB_M(m);
   double *T = w.wn;             // [col][m] upper triangle -> R
   double *Ri = w.wn + m * m;    // [col][m] upper triangle: R^-1
   lb_prep_ld(w, m, col);
@@ -466,7 +482,7 @@ LB_NI double lb_projgr(int n, const int *nbd, const double *lo, const double *hi
 // the Cauchy point in w.z; w.c receives W'(xcp - x).  Instead of the heap of the original
 // (hpsolb) the next breakpoint is a warp arg-min over the remaining ones.
 LB_FN int lb_cauchy(const LbParams &P, LbWork &w, const LbScal &s, int &nseg_out) {
-  const int n = P.n, m = P.m, col = s.col, col2 = 2 * col, ldw = LB_LDW(m);
+  const int n = P.n, m = LB_M(P.m), col = s.col, col2 = 2 * col, ldw = LB_LDW(m);
   const double theta = s.theta;
   LbDP tb = w.t, d = w.d, xcp = w.z;
   nseg_out = 0;
@@ -700,7 +716,7 @@ LB_FN int lb_formk_code(int o, int m) {
 //   lb_gram_sym : sum_i v_a(i) v_b(i), a >= b, for the column block starting at `coff`
 //   lb_gram_sy  : sum_i s_a(i) y_b(i) for a in [A0, A0 + LB_MMAX/2)
 LB_FN void lb_gram_sym(const LbParams &P, const LbWork &w, int col, int coff, double *out) {
-  const int n = P.n, ldw = LB_LDW(P.m);
+  const int n = P.n, ldw = LB_LDW(LB_M(P.m));
   double acc[LB_MMAX * (LB_MMAX + 1) / 2];
 #pragma unroll
   for (int e = 0; e < LB_MMAX * (LB_MMAX + 1) / 2; ++e) acc[e] = 0.0;
@@ -721,7 +737,7 @@ LB_FN void lb_gram_sym(const LbParams &P, const LbWork &w, int col, int coff, do
 }
 template <int A0>
 LB_FN void lb_gram_sy(const LbParams &P, const LbWork &w, int col, double *out) {
-  const int n = P.n, m = P.m, ldw = LB_LDW(P.m);
+  const int n = P.n, m = LB_M(P.m), ldw = LB_LDW(LB_M(P.m));
   constexpr int NA = LB_MMAX / 2;
   double acc[NA * LB_MMAX];
 #pragma unroll
@@ -746,7 +762,7 @@ LB_FN void lb_gram_sy(const LbParams &P, const LbWork &w, int col, double *out) 
 #endif
 
 LB_FN int lb_formk(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
-  const int n = P.n, m = P.m, col = s.col, ldw = LB_LDW(m), ldn = 2 * m;
+  const int n = P.n, m = LB_M(P.m), col = s.col, ldw = LB_LDW(m), ldn = 2 * m;
   const double theta = s.theta;
   LB_SYNC();
 #if LB_WARP
@@ -917,7 +933,7 @@ LB_FN int lb_formk(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
 // ------------------------------------------------------------------ reduced gradient (cmprlb)
 // r[k] = -(B(xcp - x) + g)[k] for free k (0 elsewhere); uses c = W'(xcp - x) from cauchy.
 LB_FN int lb_cmprlb(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
-  const int n = P.n, m = P.m, col = s.col, ldw = LB_LDW(m);
+  const int n = P.n, m = LB_M(P.m), col = s.col, ldw = LB_LDW(m);
   const double theta = s.theta;
   LB_SYNC();
   if (!P.cnstnd && col > 0) {
@@ -945,7 +961,7 @@ LB_FN int lb_cmprlb(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
 // ------------------------------------------------------------------ subspace minimisation (subsm, v3.0)
 // In: w.z = Cauchy point, w.r = reduced gradient.  Out: w.z = subspace minimiser.
 LB_FN int lb_subsm(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
-  const int n = P.n, m = P.m, col = s.col, col2 = 2 * col, ldw = LB_LDW(m), ldn = 2 * m;
+  const int n = P.n, m = LB_M(P.m), col = s.col, col2 = 2 * col, ldw = LB_LDW(m), ldn = 2 * m;
   const double theta = s.theta;
   if (nfree <= 0) return 0;
   double *wv = w.v;
@@ -1074,7 +1090,7 @@ LB_FN int lb_subsm(const LbParams &P, LbWork &w, const LbScal &s, int nfree) {
 // shifted by one instead of rotating a head pointer.  On entry w.r = y (new), w.d = s (new),
 // rr = y'y, dr = y's.  SY, SS and YY are maintained as full matrices (see LbWork).
 LB_FN void lb_matupd(const LbParams &P, LbWork &w, LbScal &s, double rr, double dr) {
-  const int n = P.n, m = P.m, ldw = LB_LDW(m);
+  const int n = P.n, m = LB_M(P.m), ldw = LB_LDW(m);
   LB_SYNC();
   if (s.iupdat <= m) {
     s.col = s.iupdat;
@@ -1169,7 +1185,7 @@ struct LbNoMem {
 // without touching the limited-memory matrices; 2 = HEAVY: resume there.
 template <class Mem>
 LB_FN int lb_advance(const LbParams &P, LbWork &w, LbScal &s, Mem &mem, int stage = 0) {
-  const int n = P.n, m = P.m;
+  const int n = P.n, m = LB_M(P.m);
   enum { ST_TESTS, ST_ITER, ST_REQUEST, ST_FAIL };
   int st;
 
