@@ -179,7 +179,8 @@ LB_FN void lb_carve(LbWork &w, double *dbase, int *ibase, int n, int m) {
   w.t = q; q += nv; w.r = q; q += nv; w.d = q; q += nv; w.z = q; q += nv;
   w.W = q; q += LB_NW(n, m);
   w.sy = q; q += m * m; w.ss = q; q += m * m; w.yy = q; q += m * m; w.tinv = q; q += m * m;
-  w.ld = q; q += m * m;
+  w.ld = q;
+  q = dbase + LB_PERSIST_DOUBLES(n, m);  // scratch starts behind the (padded) persisted block
   w.x = q; q += nv; w.g = q; q += nv; w.xp = q; q += nv;
   w.wn = q; q += 4 * m * m;
   w.rd = q; q += 2 * m;

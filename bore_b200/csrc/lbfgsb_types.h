@@ -72,8 +72,10 @@ struct LbScal {
 #define LB_SCAL_DOUBLES 32
 #define LB_NV(n) (((n) + 1) & ~1)
 #define LB_NW(n, m) (((n) * LB_LDW(m) + 1) & ~1)
+// (rounded up to an even count: the block is moved by bulk copies whose size must be a multiple
+// of 16 bytes -- 5 m^2 is odd for odd m)
 #define LB_PERSIST_DOUBLES(n, m) \
-  (LB_SCAL_DOUBLES + 4 * LB_NV(n) + LB_NW(n, m) + LB_NPERSIST_MM * (m) * (m))
+  ((LB_SCAL_DOUBLES + 4 * LB_NV(n) + LB_NW(n, m) + LB_NPERSIST_MM * (m) * (m) + 1) & ~1)
 
 // ------------------------------------------------------------------ More'-Thuente step (dcstep)
 LB_HD void lb_dcstep(double &stx, double &fx, double &dx, double &sty, double &fy, double &dy,

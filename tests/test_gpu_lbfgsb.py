@@ -188,3 +188,43 @@ def test_maxiter_limit_status():
     assert np.all((got["status"] == 1) == (got["nit"] == 3) | (got["status"] != 1))
     assert np.any(got["status"] == 1)
     assert np.all(got["task"][got["status"] == 1] == 504)
+
+
+def test_minimize_with_other_history_sizes_uses_the_generic_core():
+    """maxcor != 10 runs the core compiled with a run-time m (maxcor == 10 runs the compile-time
+    m = 10 build): both must follow SciPy with the same option."""
+    from scipy.optimize import Bounds
+    from bore_b200.engine import NativeMLP
+    name = "cfg5_plugin8"
+    dims, acts, transform = NETS[name]
+    n = dims[0]
+    w = trained_weights(dims, acts, seed=3)
+    X0 = np.random.RandomState(9).uniform(size=(96, n))
+    net = NativeMLP(dims, acts)
+    net.set_weights(w)
+    for m in (3, 7, 10):
+        got = net.lbfgsb(X0, 0.0, 1.0, transform=transform, m=m)
+        ref = am.minimize_starts(w, acts, X0, Bounds(np.zeros(n), np.ones(n)), transform=transform,
+                                 options=dict(maxiter=1000, ftol=1e-9, maxcor=m))
+        agree = np.abs(got["fun"] - ref["fun"]) <= FUN_TOL
+        print("maxcor", m, "agree", agree.mean(), "nit equal", np.mean(got["nit"] == ref["nit"]))
+        assert agree.mean() >= 0.97, (m, agree.mean())
+        assert np.mean(got["nit"] == ref["nit"]) >= 0.85
+    # a ReLU net, where the history size changes the path of nearly every start (SciPy: nit differs
+    # on 98 % of the starts between maxcor 3 and 10): the option must reach the device, and the
+    # agreement is held to the reference's own self-agreement as everywhere on ReLU objectives
+    name = "cfg2_hartmann6"
+    dims, acts, transform = NETS[name]
+    n = dims[0]
+    w = trained_weights(dims, acts, seed=3)
+    X0 = np.random.RandomState(9).uniform(size=(96, n))
+    net = NativeMLP(dims, acts)
+    net.set_weights(w)
+    nits = {}
+    for m in (3, 10):
+        got = net.lbfgsb(X0, 0.0, 1.0, transform=transform, m=m)
+        ref = am.minimize_starts(w, acts, X0, Bounds(np.zeros(n), np.ones(n)), transform=transform,
+                                 options=dict(maxiter=1000, ftol=1e-9, maxcor=m))
+        nits[m] = got["nit"]
+        _check_against_self_agreement(f"{name} maxcor={m}", got, ref, w, acts, transform, X0, n)
+    assert np.mean(nits[3] != nits[10]) >= 0.5
