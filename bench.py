@@ -486,7 +486,7 @@ def run_cfg4(args, rank, local_rank, world):
         model._net.reset_optimizer()
         model.fit(X, z, batch_size=B, epochs=E, permutations=perms)
         res = model.argmax([(0.0, 1.0)] * D, num_starts=K, num_samples=P, X_init=X_init)
-        return model._last_stats["evals"], sum(r is not None for r in res)
+        return model._last_stats["evals"], int(res.found.sum())
 
     def barrier():
         if world > 1:

@@ -58,6 +58,42 @@ class LazyLoss:
         return repr(self.numpy())
 
 
+class BatchedResults:
+    """One ``OptimizeResult`` (or None) per problem, as a read-only sequence over the arrays that
+    came back from the GPU: ``res[p]`` / iteration build the reference's per-problem objects on
+    demand (4,096 of them cost more host time than the transfer), the bulk views ``found``, ``x``,
+    ``fun``, ``nit``, ``nfev``, ``status`` serve callers that want all problems at once."""
+
+    def __init__(self, rec, dim):
+        self._rec, self._dim = rec, dim
+        self.found = rec[:, dim + 5] != 0              # False: no start of the problem qualified
+        self.x = rec[:, :dim]
+        self.fun = rec[:, dim].astype(np.float32)
+        self.nit = rec[:, dim + 1].astype(np.int64)
+        self.nfev = rec[:, dim + 2].astype(np.int64)
+        self.status = rec[:, dim + 3].astype(np.int64)
+        self._task = rec[:, dim + 4].astype(np.int64)
+
+    def __len__(self):
+        return self._rec.shape[0]
+
+    def __getitem__(self, p):
+        if isinstance(p, slice):
+            return [self[i] for i in range(*p.indices(len(self)))]
+        if p < 0:
+            p += len(self)
+        if not 0 <= p < len(self):
+            raise IndexError(p)
+        if not self.found[p]:
+            return None
+        st, nfev = int(self.status[p]), int(self.nfev[p])
+        return OptimizeResult(x=self.x[p].copy(), fun=self.fun[p], nit=int(self.nit[p]), nfev=nfev, njev=nfev,
+                              status=st, success=bool(st == 0), message=lbfgsb_message(st, int(self._task[p])))
+
+    def __iter__(self):
+        return (self[p] for p in range(len(self)))
+
+
 class BatchedMaximizableSequential:
 
     def __init__(self, layers, n_problems, transform=ops.identity, seed=None, device=None):
@@ -164,7 +200,8 @@ class BatchedMaximizableSequential:
     def argmax(self, bounds, num_starts=5, num_samples=1024, method="L-BFGS-B",
                options=dict(maxiter=1000, ftol=1e-9), random_state=None, X_init=None,
                exclude=None, rtol=1e-5, atol=1e-8):
-        """One ``OptimizeResult`` (or None) per problem: bore/mixins.py:22-89 for each of them.
+        """One ``OptimizeResult`` (or None) per problem (``BatchedResults``, a lazy sequence):
+        bore/mixins.py:22-89 for each of them.
         ``random_state`` draws the (M, num_samples, D) screening samples problem after problem
         (what M sequential ``argmax`` calls sharing one RandomState would consume); ``X_init``
         overrides the draw.  ``exclude`` (M, N, D): each problem's stored observations -- results
@@ -210,14 +247,4 @@ class BatchedMaximizableSequential:
         rec = torch.cat([xw, pick(res["fun"]).unsqueeze(-1)] +
                         [pick(res[k]).to(torch.float64).unsqueeze(-1) for k in ("nit", "nfev", "status", "task")] +
                         [keys.to(torch.float64).unsqueeze(-1)], dim=1).cpu().numpy()
-        out = []
-        for p in range(M):
-            r = rec[p]
-            if r[dim + 5] == 0:
-                out.append(None)
-                continue
-            st, task = int(r[dim + 3]), int(r[dim + 4])
-            out.append(OptimizeResult(x=r[:dim].copy(), fun=np.float32(r[dim]), nit=int(r[dim + 1]),
-                                      nfev=int(r[dim + 2]), njev=int(r[dim + 2]), status=st,
-                                      success=bool(st == 0), message=lbfgsb_message(st, task)))
-        return out
+        return BatchedResults(rec, dim)

@@ -138,7 +138,10 @@ class NativeMLP:
                         del pool[i]
                         break
         view = best[0][:nbytes].view(tdt).reshape(a.shape)
-        np.copyto(view.numpy(), a, casting="unsafe")
+        if nbytes >= (1 << 22) and a.flags.writeable and a.dtype.kind in "fiub":
+            view.copy_(torch.from_numpy(a))  # large arrays: torch converts / copies on all host cores
+        else:
+            np.copyto(view.numpy(), a, casting="unsafe")
         out = view.to(self._tdev(), non_blocking=True)
         best[1].record(torch.cuda.current_stream(self.device))
         return out
