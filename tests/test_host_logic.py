@@ -138,3 +138,70 @@ def test_maybe_distort():
     assert out.shape == (2,) and np.all(out >= 0) and np.all(out <= 1) and len(msgs) == 1
     with pytest.raises(AssertionError):
         maybe_distort(loc, 0.05)
+
+
+# ---------------------------------------------------------------- host-side containers (no GPU)
+def test_batched_results_is_a_lazy_sequence_of_optimize_results():
+    from bore_b200.batched import BatchedResults
+    dim = 3
+    #        x0   x1   x2   fun  nit nfev status task key
+    rec = np.array([[.1, .2, .3, -0.5, 7, 9, 0, 1, 5.0],
+                    [.4, .5, .6, -0.1, 3, 4, 1, 3, 9.0],
+                    [.0, .0, .0, 0.0, 0, 0, 2, 0, 0.0]])      # key 0: no start qualified
+    res = BatchedResults(rec, dim)
+    assert len(res) == 3 and list(res.found) == [True, True, False]
+    r0, r1, r2 = res[0], res[1], res[-1]
+    assert r2 is None and res[2] is None
+    assert np.array_equal(r0.x, [.1, .2, .3]) and r0.fun == np.float32(-0.5) and r0.nit == 7 and r0.nfev == 9
+    assert r0.success and r0.status == 0 and not r1.success and r1.status == 1
+    assert isinstance(r0.message, str) and r0.x is not res.x          # a copy, not a view
+    assert [r is None for r in res] == [False, False, True]
+    assert len(res[0:2]) == 2
+    with pytest.raises(IndexError):
+        res[3]
+
+
+def test_lazy_loss_behaves_like_its_array():
+    import torch
+    from bore_b200.batched import LazyLoss
+    a = np.arange(6, dtype=np.float32).reshape(2, 3)
+    l = LazyLoss(torch.from_numpy(a.copy()))
+    assert l.shape == (2, 3) and len(l) == 2
+    np.testing.assert_array_equal(l, a)
+    np.testing.assert_array_equal(l[:, 0], a[:, 0])
+    assert np.all(np.isfinite(l)) and np.asarray(l, np.float64).dtype == np.float64
+    assert [row.tolist() for row in l] == a.tolist()
+
+
+def test_unique_filter_host_predicate_is_the_reference_rule():
+    """UniqueFilter called as a function = not Record.is_duplicate (bore/plugins/hpbandster/base.py:227-231)."""
+    from scipy.optimize import OptimizeResult
+    from bore_b200.data import Record, UniqueFilter
+    rec = Record()
+    f = UniqueFilter(rec)
+    assert f.stored().shape[0] == 0 and f(OptimizeResult(x=np.array([.5, .5])))
+    rec.append(np.array([.5, .5]), 1.0)
+    rec.append(np.array([.1, .9]), 2.0)
+    assert f.stored().shape == (2, 2)
+    assert not f(OptimizeResult(x=np.array([.5, .5 + 1e-9])))
+    assert f(OptimizeResult(x=np.array([.5, .5 + 1e-3])))
+
+
+def test_svgd_host_pieces_match_the_reference_definitions():
+    """rank / distortions (bore/optimizers/svgd/base.py:11-64) are host helpers; the SVGD arithmetic
+    itself is device-only (tests/test_svgd.py)."""
+    from bore_b200.optimizers.svgd.base import (SVGD, DistortionConstant, DistortionExpDecay, rank)
+    from bore_b200.optimizers.svgd.kernels import RadialBasis
+    from oracle import svgd as osv
+    a = np.random.RandomState(0).rand(17)
+    a[3] = a[5]
+    np.testing.assert_array_equal(rank(a), osv.rank(a))
+    assert DistortionConstant(2.5)(rank(a)) == 2.5
+    np.testing.assert_array_equal(DistortionExpDecay(0.7)(rank(a)), np.power(rank(a), -0.7))
+    s = SVGD(kernel=RadialBasis(length_scale=None), distortion=DistortionExpDecay(2.0))
+    o = s._device_options()
+    assert np.isnan(o["length_scale"]) and o["lambd"] == 2.0
+    o = SVGD(kernel=RadialBasis(0.5), distortion=DistortionConstant(3.0))._device_options()
+    assert o["length_scale"] == 0.5 and np.isnan(o["lambd"]) and o["zeta_c"] == 3.0
+    with pytest.raises(NotImplementedError):
+        SVGD(kernel=object())._device_options()
