@@ -80,6 +80,19 @@ def make_problem(wl, seed):
     return X, z, perms
 
 
+def glorot_init(dims, seed):
+    """Keras-ordered weights [W0 (in,out), b0, W1, b1, ...]: glorot_uniform kernels from
+    RandomState(seed), zero biases -- the synthetic random-init weights of both arms (spelled out here
+    so that the GPU arm imports nothing from oracle/)."""
+    rs = np.random.RandomState(seed)
+    ws = []
+    for fi, fo in zip(dims[:-1], dims[1:]):
+        lim = np.sqrt(6.0 / (fi + fo))
+        ws.append(rs.uniform(-lim, lim, size=(fi, fo)).astype(np.float32))
+        ws.append(np.zeros(fo, np.float32))
+    return ws
+
+
 def flops_per_eval(dims):
     return 4 * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
 
@@ -227,14 +240,13 @@ def run_ours(args, wl, rank, local_rank, world):
     from bore_b200.layers import Dense
     from bore_b200.models import MaximizableSequential
     from bore_b200 import distributed as bd
-    from oracle import keras_mlp as km  # init weights only (Glorot with a seed) + cpu_baseline
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     lib = _lib.require_cuda()
     dims, acts, D, S = wl["dims"], wl["acts"], wl["dims"][0], wl["starts"]
     X, z, perms = make_problem(wl, seed=0)              # the same problem on every rank
-    w0 = km.init_weights(dims, 0)
+    w0 = glorot_init(dims, 0)
     model = MaximizableSequential(transform=ops.TRANSFORMS[wl["transform"]], device=local_rank)
     for i, (u, a) in enumerate(zip(dims[1:], acts)):
         model.add(Dense(u, activation=a, input_dim=D if i == 0 else None))
@@ -461,7 +473,6 @@ def run_cfg4(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
     from bore_b200 import BatchedMaximizableSequential, Dense, problem_shard
-    from oracle import keras_mlp as km
     torch.cuda.set_device(local_rank)
     total, N, D, E, B, K, P = 4096, 500, 6, 125, 64, 5, 1024
     lo_p, hi_p = problem_shard(total, rank, world)
@@ -477,7 +488,7 @@ def run_cfg4(args, rank, local_rank, world):
               Dense(1, activation="sigmoid")]
     model = BatchedMaximizableSequential(layers, n_problems=M, seed=rank, device=local_rank)
     model.compile(optimizer="adam", loss="binary_crossentropy")
-    model.set_weights([km.init_weights(dims, 1000 + lo_p + p) for p in range(M)])
+    model.set_weights([glorot_init(dims, 1000 + lo_p + p) for p in range(M)])
     params = model._net.params_tensor()
     w0d = params.clone()
 

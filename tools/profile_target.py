@@ -6,13 +6,12 @@ import numpy as np
 import torch
 import bench
 from bore_b200.engine import NativeMLP
-from oracle import keras_mlp as km
 
 wl = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "cfg3"]
 S = int(sys.argv[2]) if len(sys.argv) > 2 else wl["starts"]
 X, z, perms = bench.make_problem(wl, 0)
 net = NativeMLP(wl["dims"], wl["acts"])
-net.set_weights(km.init_weights(wl["dims"], 0))
+net.set_weights(bench.glorot_init(wl["dims"], 0))
 net.fit(X, z, wl["epochs"], wl["batch"], perms)
 D = wl["dims"][0]
 X0 = torch.from_numpy(np.random.RandomState(1).uniform(size=(S, D))).cuda()
