@@ -238,12 +238,22 @@ __device__ __forceinline__ void fence_async_smem() {  // generic-proxy smem writ
 // overrides it (-1 = free-running).
 constexpr int LB_NPHASE_MAX = 4;
 
-// the limited-memory matrices arrive with the rest of the block; what is left is the
-// bookkeeping of what has to be written back, and the phase barriers
+// A start's block is staged in two pieces: the prefix (scalars | t r d z) when the item is
+// claimed, the limited-memory part (W and the m x m matrices, 87 % of the bytes) only when the
+// light stage finds that a new iteration begins -- about half of all steps just continue a line
+// search and never touch it.  The kernel requests the second piece right before the rendezvous
+// (whose wait hides the latency); load() -- the hook lb_advance calls where the matrices are first
+// needed -- waits for it.  The rest is bookkeeping of what has to be written back, and the phase
+// barriers.
 struct BlockMem {
-  bool loaded = false, is_dirty = false, vec_dirty = false;
+  bool loaded = false, is_dirty = false, vec_dirty = false, requested = false;
   int nph = 0, cap = LB_NPHASE_MAX;
-  __device__ void load() { loaded = true; }
+  uint64_t *bar = nullptr;  // mbarrier of the second piece, and the parity of its current phase
+  uint32_t parity = 0;
+  __device__ void load() {
+    if (!loaded && requested) { mbar_wait(bar, parity); __syncwarp(); }
+    loaded = true;
+  }
   __device__ void dirty() { is_dirty = true; }
   __device__ void dirty_vec() { vec_dirty = true; }
   // every warp of the CTA passes exactly `cap` of these per heavy pass (the kernel pads);
@@ -253,10 +263,10 @@ struct BlockMem {
   }
 };
 
-// CTA header in dynamic shared memory: formk output map | lo | hi | nbd | one mbarrier per warp
+// CTA header in dynamic shared memory: formk output map | lo | hi | nbd | two mbarriers per warp
 __host__ __device__ inline size_t lb_header_bytes(int n, int wpb) {
   return align_up(LB_FORMK_ACC * 32 * sizeof(int), 16) + 2 * align_up(n * sizeof(double), 16) +
-         align_up(n * sizeof(int), 16) + align_up(wpb * sizeof(uint64_t), 16);
+         align_up(n * sizeof(int), 16) + align_up(2 * wpb * sizeof(uint64_t), 16);
 }
 
 // One round.  Work items (positions of the round's active list) are claimed dynamically from a
@@ -287,9 +297,12 @@ __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t w
   int *s_nbd = reinterpret_cast<int *>(s_hi + align_up(n * sizeof(double), 16) / sizeof(double));
   uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(s_nbd) +
                                                 align_up(n * sizeof(int), 16));
-  uint64_t *bar = bars + wib;
+  uint64_t *bar = bars + 2 * wib, *bar2 = bar + 1;
   unsigned char *base = smem_raw + lb_header_bytes(n, wpb) + warp_bytes * wib;
   const uint32_t block_bytes = (uint32_t)(LB_PERSIST_DOUBLES(n, m) * sizeof(double));
+  // first piece: scalars | t r d z; second piece: W and the matrices (both multiples of 16 bytes)
+  const uint32_t p1_bytes = (uint32_t)(SCAL_BYTES + 4 * LB_NV(n) * sizeof(double));
+  const uint32_t p2_bytes = block_bytes - p1_bytes;
 
   // claim a position of the active list (>= n_active: the list is exhausted)
   auto claim = [&]() {
@@ -302,10 +315,11 @@ __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t w
   int cur_i = claim();
   if (lane == 0) {
     mbar_init(bar, 1);
+    mbar_init(bar2, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (cur_i < n_active) {
-      mbar_expect_tx(bar, block_bytes);
-      bulk_g2s(base, D.blocks + D.block_stride * list_cur[cur_i], block_bytes, bar);
+      mbar_expect_tx(bar, p1_bytes);
+      bulk_g2s(base, D.blocks + D.block_stride * list_cur[cur_i], p1_bytes, bar);
     }
   }
   int nxt_i = n_active;
@@ -328,7 +342,7 @@ __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t w
   LbScal *s_smem = reinterpret_cast<LbScal *>(base);
   const FG *F = static_cast<const FG *>(D.F);
   const FG *G = static_cast<const FG *>(D.G);
-  uint32_t parity = 0;
+  uint32_t parity = 0, parity2 = 0;
   unsigned long long my_bytes = 0, my_evals = 0;
 
   LbScal s;
@@ -340,6 +354,10 @@ __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t w
   auto finish = [&](int pend) {
     char *gblock = D.blocks + D.block_stride * sid;
     double *xr = D.xreq + (size_t)sid * n;
+    if (mem.requested) {  // the second piece must have landed before its workspace is reused
+      if (!mem.loaded) mbar_wait(bar2, parity2);
+      parity2 ^= 1;
+    }
     __syncwarp();
     my_bytes += step_bytes(n, (int)sizeof(FG), was_ls, mem.loaded, col_in, s.col, pend != 0, mem.is_dirty);
     if (pend) {
@@ -377,8 +395,8 @@ __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t w
       // the workspace may be overwritten once the store has read it
       bulk_wait_read();
       if (cur_i < n_active) {
-        mbar_expect_tx(bar, block_bytes);
-        bulk_g2s(base, D.blocks + D.block_stride * list_cur[cur_i], block_bytes, bar);
+        mbar_expect_tx(bar, p1_bytes);
+        bulk_g2s(base, D.blocks + D.block_stride * list_cur[cur_i], p1_bytes, bar);
       }
     }
     __syncwarp();
@@ -394,7 +412,7 @@ __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t w
       // claim the item after this one and pull its block into L2 meanwhile
       nxt_i = claim();
       if (lane == 0 && nxt_i < n_active)
-        bulk_prefetch_l2(D.blocks + D.block_stride * list_cur[nxt_i], block_bytes);
+        bulk_prefetch_l2(D.blocks + D.block_stride * list_cur[nxt_i], p1_bytes);
       const double *xr = D.xreq + (size_t)sid * n;
       const FG *gr = G + (size_t)sid * n;
       const double fval = (double)F[sid];
@@ -412,10 +430,21 @@ __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t w
       s.f = fval;
       mem = BlockMem();
       mem.cap = nphase < 0 ? 0 : nphase;
+      mem.bar = bar2;
+      mem.parity = parity2;
       col_in = s.col;
       was_ls = s.phase == LB_PH_LNSRCH;
       const int r = LbCore<MC>::advance(P, w, s, mem, 1);
-      if (r == 2) { holding = true; break; }
+      if (r == 2) {
+        // a new iteration begins: request W and the matrices now, wait in mem.load()
+        if (lane == 0) {
+          mbar_expect_tx(bar2, p2_bytes);
+          bulk_g2s(base + p1_bytes, D.blocks + D.block_stride * sid + p1_bytes, p2_bytes, bar2);
+        }
+        mem.requested = true;
+        holding = true;
+        break;
+      }
       finish(r);
     }
     if (nphase < 0) {  // free-running warps (no alignment at all): tuning / comparison mode
