@@ -24,7 +24,7 @@ def test_math_against_reference(gold):
         assert isinstance(bm.steps_per_epoch(n, b), int)
     for a, b, want in gold["ceil_divide"]:
         assert int(bm.ceil_divide(a, b)) == want
-    assert doctest.testmod(bm).failed == 0  # the reference's doctests (bore/math.py:15-27)
+    assert doctest.testmod(bm).failed == 0  # same function as the doctests of bore/math.py:15-27
 
 
 def test_from_bounds_against_reference(gold):
