@@ -92,9 +92,10 @@ def load(build_if_missing=True):
         if _lib is not None:
             return _lib
         path = _build.LIB_PATH
-        if not os.path.exists(path):
+        if not os.path.exists(path) or _build.needs_build():
+            # a library older than csrc/ or the header is never loaded silently
             if not build_if_missing:
-                raise BoreNativeError(f"{path} is missing; run `python -m bore_b200.build`")
+                raise BoreNativeError(f"{path} is missing or stale; run `python -m bore_b200.build`")
             _build.build_library()
         lib = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():

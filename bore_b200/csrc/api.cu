@@ -108,6 +108,9 @@ int bore_mlp_num_models(const bore_mlp *h) { return h ? h->n_models : -1; }
 int bore_mlp_set_weights(bore_mlp *h, int model, const float *params_host) {
   CHECK_MODEL(h, model);
   const size_t nb = (size_t)h->desc.n_params * sizeof(float);
+  // fit / argmax run on the caller's streams, which a legacy-stream copy is not ordered against
+  // when they are non-blocking: drain the device first (parameter I/O is rare)
+  BORE_CUDA(cudaDeviceSynchronize());
   BORE_CUDA(cudaMemcpy(h->params + (size_t)model * h->desc.n_params, params_host, nb,
                        cudaMemcpyHostToDevice));
   return 0;
@@ -116,6 +119,7 @@ int bore_mlp_set_weights(bore_mlp *h, int model, const float *params_host) {
 int bore_mlp_get_weights(bore_mlp *h, int model, float *params_host) {
   CHECK_MODEL(h, model);
   const size_t nb = (size_t)h->desc.n_params * sizeof(float);
+  BORE_CUDA(cudaDeviceSynchronize());  // see bore_mlp_set_weights
   BORE_CUDA(cudaMemcpy(params_host, h->params + (size_t)model * h->desc.n_params, nb,
                        cudaMemcpyDeviceToHost));
   return 0;
@@ -125,6 +129,7 @@ int bore_mlp_set_adam_state(bore_mlp *h, int model, const float *m_host, const f
                             int64_t iterations) {
   CHECK_MODEL(h, model);
   const size_t np = h->desc.n_params, nb = np * sizeof(float);
+  BORE_CUDA(cudaDeviceSynchronize());
   BORE_CUDA(cudaMemcpy(h->adam_m + model * np, m_host, nb, cudaMemcpyHostToDevice));
   BORE_CUDA(cudaMemcpy(h->adam_v + model * np, v_host, nb, cudaMemcpyHostToDevice));
   long long t = iterations;
@@ -136,6 +141,7 @@ int bore_mlp_get_adam_state(bore_mlp *h, int model, float *m_host, float *v_host
                             int64_t *iterations) {
   CHECK_MODEL(h, model);
   const size_t np = h->desc.n_params, nb = np * sizeof(float);
+  BORE_CUDA(cudaDeviceSynchronize());
   BORE_CUDA(cudaMemcpy(m_host, h->adam_m + model * np, nb, cudaMemcpyDeviceToHost));
   BORE_CUDA(cudaMemcpy(v_host, h->adam_v + model * np, nb, cudaMemcpyDeviceToHost));
   long long t = 0;

@@ -585,13 +585,18 @@ int setup_params(LbDev &D, const LbLayout &L, char *work, int S, int n, int m, c
 // one round of the stepper
 template <typename FG, int MC>
 int launch_round_mc(const LbDev &D, const StepLaunch &SL, int round, int nphase, cudaStream_t stream) {
-  static bool attr_done = false;  // one flag per instantiation
-  if (!attr_done) {  // opt in to > 48 KB of dynamic shared memory (once per kernel)
+  // opt in to > 48 KB of dynamic shared memory: the attribute belongs to the DEVICE's context,
+  // so one flag per instantiation and device
+  static bool attr_done[64] = {};
+  int dev = 0;
+  BORE_CUDA(cudaGetDevice(&dev));
+  if (dev >= 64 || !attr_done[dev]) {
     BORE_CUDA(cudaFuncSetAttribute(lbfgsb_warp_kernel<FG, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    227 * 1024));
-    attr_done = true;
+    if (dev < 64) attr_done[dev] = true;
   }
   lbfgsb_warp_kernel<FG, MC><<<SL.grid, SL.block, SL.smem, stream>>>(D, round, SL.warp_bytes, nphase);
+  BORE_CUDA(cudaGetLastError());
   return 0;
 }
 

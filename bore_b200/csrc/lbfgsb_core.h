@@ -1191,6 +1191,25 @@ LB_FN int lb_advance(const LbParams &P, LbWork &w, LbScal &s, Mem &mem, int stag
   int st;
 
   if (s.phase == LB_PH_DONE) return 0;
+  if (stage != 2) {
+    // Non-finite objective or gradient (transform = exp overflowing fp32, a caller's objective
+    // returning NaN): SciPy's line search degenerates on such values and ends ABNORMAL, and the
+    // reference's argmax drops abnormal results (bore/mixins.py:83-85).  End the start here with
+    // the same status; inside a line search the previous iterate is restored first, as the
+    // original does when the search fails.
+    int bad = !(fabs(s.f) <= DBL_MAX);
+    LB_FOR(i, n) bad |= !(fabs(w.g[i]) <= DBL_MAX);
+    if (lb_any(bad)) {
+      if (s.phase == LB_PH_LNSRCH) {
+        LB_SYNC();
+        LB_FOR(i, n) { w.x[i] = w.t[i]; w.g[i] = w.r[i]; }
+        s.f = s.fold;
+        LB_SYNC();
+      }
+      lb_finish(s, 2, 0);
+      return 0;
+    }
+  }
   if (stage == 2) {
     st = s.resume;
   } else if (s.phase == LB_PH_START) {

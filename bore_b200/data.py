@@ -71,6 +71,18 @@ class UniqueFilter:
             self.logger.warning("Duplicate detected! Skipping...")
         return not dup
 
+    def report_dropped(self, keep_dev):
+        """Device path: one warning per duplicate that the keep mask dropped -- the lines the
+        reference logs from its per-result callback (plugins/hpbandster/base.py:227-231).  The
+        mask is only read back when somebody listens."""
+        if self.logger is None:
+            return
+        enabled = getattr(self.logger, "isEnabledFor", None)
+        if enabled is not None and not enabled(30):  # logging.WARNING
+            return
+        for _ in range(int((keep_dev == 0).sum().item())):
+            self.logger.warning("Duplicate detected! Skipping...")
+
     def stored(self):
         """(N, D) float64 matrix of the stored feature vectors (N may be 0)."""
         if not self.record.features:

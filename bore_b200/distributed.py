@@ -84,7 +84,9 @@ def global_winner(key, record_fn, total, record_len, group=None):
     else:
         rec = torch.empty(record_len, dtype=torch.float64, device=key.device)
     if world > 1:
-        dist.broadcast(rec, src=owner, group=group)
+        # `owner` is a rank WITHIN `group`; broadcast wants a global rank
+        src = dist.get_global_rank(group, owner) if group is not None else owner
+        dist.broadcast(rec, src=src, group=group)
     return gidx, rec
 
 

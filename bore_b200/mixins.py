@@ -132,15 +132,15 @@ class MaximizableMixin:
         from .data import UniqueFilter
         on_device = filter_fn is _accept_all or isinstance(filter_fn, UniqueFilter)
         if print_fn is not None or not on_device:
-            # reference semantics on the materialised list; filter_fn is consulted lazily in
-            # ascending (fun, index) order, which selects the same result as the reference's scan
-            results = self.maxima(bounds, print_fn=print_fn, **kw)
-            order = sorted(range(len(results)), key=lambda i: (results[i].fun, i))
-            for i in order:
-                res = results[i]
+            # the reference's scan, verbatim (bore/mixins.py:80-87): every qualifying result is
+            # shown to filter_fn once, in index order; first strict minimum wins (a NaN `fun`
+            # never compares smaller, so it cannot win)
+            res_best = None
+            for res in self.maxima(bounds, print_fn=print_fn, **kw):
                 if (res.success or res.status == 1) and filter_fn(res):
-                    return res
-            return None
+                    if res_best is None or res.fun < res_best.fun:
+                        res_best = res
+            return res_best
         X_init, res, i0, f0 = self._maxima_device(bounds, **kw)
         if res is None:
             return OptimizeResult(x=X_init[i0], fun=f0, success=True)
@@ -152,6 +152,7 @@ class MaximizableMixin:
             if prev.shape[0] > 0:
                 keep = net.keep_unique_dev(res["x"].unsqueeze(0), net.to_device(prev[None], np.float64),
                                            rtol=filter_fn.rtol, atol=filter_fn.atol).reshape(-1)
+                filter_fn.report_dropped(keep)
         key = int(net.select_best(res["fun"], res["status"], keep_dev=keep).item())
         if key == 0:
             return None
