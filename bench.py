@@ -9,7 +9,10 @@ batched on-device L-BFGS-B.  Default workload = BASELINE.json configs[2], the co
 north_star's target is quoted on: synthetic 50-D Ackley, Dense64 x3 (+ sigmoid output), 2,000
 observations, 65,536 starts per GPU.  Multi-GPU is WEAK scaling: weights replicated (every rank
 runs the same deterministic fit), every rank optimises its own 65,536 starts, one NCCL max
-all-reduce on the packed (value, index) key picks the global argmax.
+all-reduce on the packed (value, index) key picks the global argmax.  The same JSON line carries
+two sub-records: `strong` (the SAME 65,536 starts in total split over the N ranks, 3 steps --
+north_star's "fit + 65,536-start argmax" from 1 to 8 GPUs) and `cfg4` (BASELINE.json configs[3]:
+4,096 independent BO problems split over the ranks, 2 steps).
 
 `value` = value+input-gradient evaluations per second, whole job, inputs resident in HBM,
 timed with CUDA events (max over ranks).  `e2e` = the same through the public Python API
@@ -91,6 +94,13 @@ def glorot_init(dims, seed):
         ws.append(rs.uniform(-lim, lim, size=(fi, fo)).astype(np.float32))
         ws.append(np.zeros(fo, np.float32))
     return ws
+
+
+def workload_config(wl):
+    """The `config` object of the JSON line -- the SAME dict for both arms (--impl ours / reference);
+    anything descriptive goes under `notes`."""
+    return {"workload": wl["name"], "starts_per_gpu": wl["starts"], "observations": wl["N"],
+            "adam_steps": wl["epochs"] * (-(-wl["N"] // wl["batch"]))}
 
 
 def flops_per_eval(dims):
@@ -217,8 +227,7 @@ def run_reference(args, wl, rank, world):
         "unit": "evals/s", "n_gpus": args.gpus, "steps": K, "warmup": args.warmup,
         "ms_per_step": 1e3 * (tf + ta) / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 MLP / f64 L-BFGS-B", "data": "synthetic",
-        "config": {"workload": wl["name"], "starts_per_gpu": wl["starts"], "observations": wl["N"],
-                   "adam_steps": wl["epochs"] * (-(-wl["N"] // wl["batch"]))},
+        "config": workload_config(wl),
         "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port",
                          "sample": f"full fit ({wl['epochs']} epochs, serial) + {S_ref} of "
                                    f"{wl['starts']} starts spread over {cores} processes per step; "
@@ -233,6 +242,7 @@ def run_reference(args, wl, rank, world):
 
 # ------------------------------------------------------------------------------ our arm
 def run_ours(args, wl, rank, local_rank, world):
+    import ctypes as C
     import torch
     import torch.distributed as dist
     from bore_b200 import ops, _lib
@@ -268,38 +278,73 @@ def run_ours(args, wl, rank, local_rank, world):
     params = net.params_tensor()
     w0d = params.clone()
     loss_d = torch.empty(1, wl["epochs"], dtype=torch.float32, device=dev)
-    zbuf = torch.empty(S, dtype=torch.float32, device=dev)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     opts = dict(m=10, ftol=1e-9, gtol=1e-5, maxiter=1000, maxfun=15000, maxls=20)
+    prof = np.zeros(8)
 
     def reset_state():
         params.copy_(w0d)
         net.reset_optimizer()
 
-    def step_resident(timers=None):
-        """fit -> screening predict -> batched L-BFGS-B -> first-minimum key (-> NCCL max)."""
-        reset_state()                                      # same work every step (see config)
-        if timers is not None:
-            ev[0].record()
-        net.fit_dev(Xd, zd, wl["N"], wl["batch"], wl["epochs"], pd, loss_dev=loss_d)
-        if timers is not None:
-            ev[1].record()
-        net.predict_dev(X0f, zbuf)                         # maxima's screening pass (mixins.py:50)
-        res = net.lbfgsb_dev(X0d, lo, hi, transform=tname, **opts)
-        key = net.select_best(res["fun"], res["status"], idx_offset=rank * S)
-        rec_fn = lambda i: torch.cat([res["x"][i], res["fun"][i:i + 1]])
-        gidx, rec = bd.global_winner(key, rec_fn, S * world, D + 1)
-        if timers is not None:
-            ev[2].record()
-            torch.cuda.synchronize()
-            timers["fit_ms"] += ev[0].elapsed_time(ev[1])
-            timers["argmax_ms"] += ev[1].elapsed_time(ev[2])
-        return res, gidx, rec
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def make_step(X0d_, X0f_, S_local, idx_offset, S_total):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        zbuf = torch.empty(S_local, dtype=torch.float32, device=dev)
+
+        def step(timers=None):
+            """fit -> screening predict -> batched L-BFGS-B -> first-minimum key (-> NCCL max)."""
+            reset_state()                                      # same work every step (see notes)
+            if timers is not None:
+                ev[0].record()
+            net.fit_dev(Xd, zd, wl["N"], wl["batch"], wl["epochs"], pd, loss_dev=loss_d)
+            if timers is not None:
+                ev[1].record()
+            net.predict_dev(X0f_, zbuf)                         # maxima's screening pass (mixins.py:50)
+            res = net.lbfgsb_dev(X0d_, lo, hi, transform=tname, **opts)
+            key = net.select_best(res["fun"], res["status"], idx_offset=idx_offset)
+            rec_fn = lambda i: torch.cat([res["x"][i], res["fun"][i:i + 1]])
+            gidx, rec = bd.global_winner(key, rec_fn, S_total, D + 1)
+            if timers is not None:
+                ev[2].record()
+                torch.cuda.synchronize()
+                timers["fit_ms"] += ev[0].elapsed_time(ev[1])
+                timers["argmax_ms"] += ev[1].elapsed_time(ev[2])
+            return res, gidx, rec
+        return step
+
+    def timed(step, K, warm):
+        """EXACTLY K steps between barrier + synchronize, CUDA events, max over ranks."""
+        for _ in range(warm):
+            step()
+        agg = dict(k2_ms=0.0, step_ms=0.0, rounds=0, bytes=0.0, evals=0.0, fused=0, grid=0, block=0)
+        timers = dict(fit_ms=0.0, argmax_ms=0.0)
+        lib.bore_lbfgsb_profile(1)
+        total_evals = 0
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            res, gidx, rec = step(timers)
+            total_evals += res["evals"]
+            lib.bore_lbfgsb_last_profile(prof.ctypes.data_as(C.POINTER(C.c_double)))
+            agg["k2_ms"] += prof[0]; agg["step_ms"] += prof[1]; agg["rounds"] += int(prof[2])
+            agg["bytes"] += prof[3]; agg["evals"] += prof[4]
+            agg["fused"], agg["grid"], agg["block"] = int(prof[5]), int(prof[6]), int(prof[7])
+        e1.record()
+        barrier()
+        lib.bore_lbfgsb_profile(0)
+        elapsed_ms = e0.elapsed_time(e1)
+        t = torch.tensor([elapsed_ms, float(total_evals)], dtype=torch.float64, device=dev)
+        if world > 1:
+            tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            elapsed_ms, evals_all = tmax[0].item(), tsum[1].item()
+        else:
+            evals_all = float(total_evals)
+        return elapsed_ms, evals_all, agg, timers
 
     peak_ffma = ffma_peak_tflops(local_rank)
     peaks = {}
@@ -309,51 +354,30 @@ def run_ours(args, wl, rank, local_rank, world):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)"
 
-    import ctypes as C
-
-    # ---- warm-up ----
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-    # ---- timed region: EXACTLY K steps, CUDA events, barrier + sync on both sides ----
-    lib.bore_lbfgsb_profile(1)
-    prof = np.zeros(5)
-    agg = dict(k2_ms=0.0, step_ms=0.0, rounds=0, bytes=0.0, evals=0.0)
-    timers = dict(fit_ms=0.0, argmax_ms=0.0)
+    # ---- headline: weak scaling, 65,536 starts on every GPU ----
+    K, W = args.steps, max(args.warmup, 3)
+    step_weak = make_step(X0d, X0f, S, rank * S, S * world)
     sampler = ClockSampler(local_rank)
-    total_evals = 0
-    barrier()
+    for _ in range(W):
+        step_weak()
     sampler.start()
-    t_ev0, t_ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_ev0.record()
-    for _ in range(args.steps):
-        res, gidx, rec = step_resident(timers)
-        total_evals += res["evals"]
-        lib.bore_lbfgsb_last_profile(prof.ctypes.data_as(C.POINTER(C.c_double)))
-        agg["k2_ms"] += prof[0]; agg["step_ms"] += prof[1]; agg["rounds"] += int(prof[2])
-        agg["bytes"] += prof[3]; agg["evals"] += prof[4]
-    t_ev1.record()
-    barrier()
+    elapsed_ms, evals_all, agg, timers = timed(step_weak, K, 0)
     clocks = sampler.stop()
-    lib.bore_lbfgsb_profile(0)
-    elapsed_ms = t_ev0.elapsed_time(t_ev1)
-    t = torch.tensor([elapsed_ms, float(total_evals)], dtype=torch.float64, device=dev)
-    if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        elapsed_ms, total_evals_all = tmax[0].item(), tsum[1].item()
-    else:
-        total_evals_all = float(total_evals)
-    K = args.steps
     ms_per_step = elapsed_ms / K
-    value = total_evals_all / (elapsed_ms * 1e-3)
+    value = evals_all / (elapsed_ms * 1e-3)
+
+    # ---- strong scaling: the SAME 65,536 starts in total, split over the ranks ----
+    Ks = 3
+    lo_s, hi_s = bd.shard_bounds(S, rank, world)
+    X0g = np.random.RandomState(1).uniform(size=(S, D))[lo_s:hi_s]   # same draw everywhere, own slice
+    X0gd = net.to_device(np.ascontiguousarray(X0g), np.float64)
+    step_strong = make_step(X0gd, X0gd.to(torch.float32), hi_s - lo_s, lo_s, S)
+    s_ms, s_evals, s_agg, s_tim = timed(step_strong, Ks, 1)
 
     # ---- e2e: the public API with HOST buffers (H2D/D2H inside the timed region) ----
     rs = np.random.RandomState(2000 + rank)
     e2e_steps = max(2, min(K, 3))
     reset_state()
-
     zeros = [np.zeros_like(a) for a in w0]
 
     def api_step():
@@ -369,7 +393,7 @@ def run_ours(args, wl, rank, local_rank, world):
     t0 = time.perf_counter()
     e2e_evals = 0
     for _ in range(e2e_steps):
-        r = api_step()
+        api_step()
         e2e_evals += model._last_stats["evals"]
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -382,54 +406,77 @@ def run_ours(args, wl, rank, local_rank, world):
     h2d = X.size * 4 + z.size * 4 + perms.size * 4 + S * D * 8 + 3 * n_par * 4
     d2h = wl["epochs"] * 4 + (D + 5) * 8 + 8
 
+    # ---- cfg 4 (BASELINE.json configs[3]) in short: 4,096 problems split over the ranks ----
+    del X0d, X0f, X0gd
+    cfg4 = None
+    if not args.no_cfg4:
+        cfg4 = cfg4_measure(rank, local_rank, world, steps=2, warm=1)
+
     if rank != 0:
         return
     # ---- per-kernel accounting over the timed region (CUDA events on the launch stream) ----
     F_eval = flops_per_eval(dims)
     n_adam = wl["epochs"] * (-(-wl["N"] // wl["batch"]))
-    k2_tflops = agg["evals"] * F_eval / (agg["k2_ms"] * 1e-3) / 1e12
-    step_gbs = agg["bytes"] / (agg["step_ms"] * 1e-3) / 1e9
-    fit_tflops = K * n_adam * flops_per_fit_step(dims, wl["batch"]) / (timers["fit_ms"] * 1e-3) / 1e12
     tot = timers["fit_ms"] + timers["argmax_ms"]
-    kernels = [
-        dict(name="lbfgsb_warp_kernel (K3 stepper)", bound="hbm", ms_per_step=agg["step_ms"] / K,
-             share=agg["step_ms"] / tot, launches_per_step=agg["rounds"] / K, achieved=step_gbs,
-             peak=hbm_peak, unit="GB/s", frac=step_gbs / hbm_peak, peak_source=hbm_src),
-        dict(name="mlp_eval_kernel<grad> (K2 value+input-grad)", bound="fp32_ffma",
-             ms_per_step=agg["k2_ms"] / K, share=agg["k2_ms"] / tot,
-             launches_per_step=agg["rounds"] / K, achieved=k2_tflops, peak=peak_ffma,
-             unit="TFLOP/s", frac=k2_tflops / peak_ffma,
-             peak_source="FFMA microbenchmark measured in this run (nominal %.1f)" % NOMINAL_FP32_TFLOPS,
-             frac_of_nominal=k2_tflops / NOMINAL_FP32_TFLOPS),
-        dict(name="fit_cluster_kernel (K1 fused training, 1 model = one 8-CTA cluster)",
-             bound="latency (8 SMs)",
-             ms_per_step=timers["fit_ms"] / K, share=timers["fit_ms"] / tot, launches_per_step=1,
-             achieved=fit_tflops, peak=peak_ffma * 8 / 148, unit="TFLOP/s",
-             frac=fit_tflops / (peak_ffma * 8 / 148), peak_source="8 SMs' share of the FFMA peak"),
-    ]
-    dom = max(kernels[:2], key=lambda k: k["ms_per_step"])
-    traffic = None
-    ncu_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(ncu_path):
-        try:
-            traffic = json.load(open(ncu_path)).get(dom["name"].split(" ")[0])
-        except Exception:
-            traffic = None
-    roofline = dict(kernel=dom["name"], bound=dom["bound"] if dom["bound"] == "hbm" else "fp32_ffma",
-                    achieved=dom["achieved"], peak=dom["peak"], unit=dom["unit"], frac=dom["frac"],
-                    traffic=traffic, peak_source=dom["peak_source"],
+    fit_tflops = K * n_adam * flops_per_fit_step(dims, wl["batch"]) / (timers["fit_ms"] * 1e-3) / 1e12
+    opt_ms = agg["k2_ms"] + agg["step_ms"]                     # K2 + stepper (or the fused kernel)
+    opt_tflops = agg["evals"] * F_eval / (opt_ms * 1e-3) / 1e12
+    step_gbs = agg["bytes"] / (agg["step_ms"] * 1e-3) / 1e9
+    ffma_src = "FFMA microbenchmark measured in this run (nominal %.1f)" % NOMINAL_FP32_TFLOPS
+    kernels = []
+    if agg["fused"]:
+        kernels.append(dict(name="lbfgsb_fused_kernel (K3f: persistent L-BFGS-B with the MLP inlined)",
+                            bound="latency", ms_per_step=agg["step_ms"] / K, share=agg["step_ms"] / tot,
+                            launches_per_step=1, achieved=opt_tflops, peak=peak_ffma, unit="TFLOP/s",
+                            frac=opt_tflops / peak_ffma, peak_source=ffma_src,
+                            hbm=dict(achieved=step_gbs, peak=hbm_peak, unit="GB/s", frac=step_gbs / hbm_peak)))
+    else:
+        k2_tflops = agg["evals"] * F_eval / (agg["k2_ms"] * 1e-3) / 1e12
+        kernels.append(dict(name="lbfgsb_warp_kernel (K3 stepper)", bound="latency", ms_per_step=agg["step_ms"] / K,
+                            share=agg["step_ms"] / tot, launches_per_step=agg["rounds"] / K, achieved=step_gbs,
+                            peak=hbm_peak, unit="GB/s", frac=step_gbs / hbm_peak, peak_source=hbm_src))
+        kernels.append(dict(name="mlp_eval_kernel<grad> (K2 value+input-grad)", bound="fp32_ffma",
+                            ms_per_step=agg["k2_ms"] / K, share=agg["k2_ms"] / tot,
+                            launches_per_step=agg["rounds"] / K, achieved=k2_tflops, peak=peak_ffma,
+                            unit="TFLOP/s", frac=k2_tflops / peak_ffma, peak_source=ffma_src,
+                            frac_of_nominal=k2_tflops / NOMINAL_FP32_TFLOPS))
+    kernels.append(dict(name="fit_cluster_kernel (K1 fused training, 1 model = one 8-CTA cluster)",
+                        bound="latency (8 SMs)", ms_per_step=timers["fit_ms"] / K, share=timers["fit_ms"] / tot,
+                        launches_per_step=1, achieved=fit_tflops, peak=peak_ffma * 8 / 148, unit="TFLOP/s",
+                        frac=fit_tflops / (peak_ffma * 8 / 148), peak_source="8 SMs' share of the FFMA peak"))
+    dom = kernels[0]
+    # The dominant kernel is LATENCY bound (ncu: issue slots ~35 % busy, HBM < 16 % busy, fp64 pipe
+    # < 10 %), so neither roofline binds; both fractions are reported: `frac` against the HBM byte
+    # model of the kernel and `fp32` = sum(nfev) * 4W FLOP over the K2 + K3 time against
+    # the FFMA peak, the roofline SURVEY.md 8(d) names for the argmax.  `traffic` is null: it is not
+    # measured inside this run (the ncu captures under profiles/ hold dram bytes per launch).
+    roofline = dict(kernel=dom["name"], bound="latency",
+                    achieved=step_gbs, peak=hbm_peak, unit="GB/s", frac=step_gbs / hbm_peak,
+                    peak_source=hbm_src, traffic=None,
+                    fp32=dict(achieved=opt_tflops, peak=peak_ffma, unit="TFLOP/s", frac=opt_tflops / peak_ffma,
+                              peak_source=ffma_src, over="K2 + K3 time of the argmax",
+                              frac_over_whole_step=(agg["evals"] * F_eval / (tot * 1e-3) / 1e12) / peak_ffma),
                     share_of_step=dom["share"], launches_per_step=dom["launches_per_step"])
+    strong = {"scaling": "strong", "n_gpus": world, "steps": Ks, "total_starts": S,
+              "starts_per_gpu": hi_s - lo_s, "ms_per_step": s_ms / Ks,
+              "value": s_evals / (s_ms * 1e-3), "unit": "evals/s",
+              "bo_iterations_per_sec": 1e3 / (s_ms / Ks),
+              "phases": {"fit_ms": s_tim["fit_ms"] / Ks, "argmax_ms": s_tim["argmax_ms"] / Ks},
+              "argmax_path": "fused persistent kernel" if s_agg["fused"] else "lock-step rounds",
+              "note": "fit is replicated on every rank (weights replicated), so it is the Amdahl term: "
+                      "speed-up <= (fit + argmax) / (fit + argmax / N)"}
     line = {
         "metric": "mlp_value_and_input_grad_evals_per_sec", "value": value, "unit": "evals/s",
-        "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 MLP / f64 L-BFGS-B", "data": "synthetic",
-        "config": {"workload": wl["name"], "starts_per_gpu": S, "observations": wl["N"],
-                   "adam_steps": n_adam, "parallelism": f"starts sharded x{world}, weights replicated",
-                   "l2_cache": "per-start L-BFGS-B state %.2f GB per GPU streams through HBM every "
-                               "round (>> 126 MB L2); no explicit flush" %
-                               (S * (256 + (4 * D + D * 21 + 500) * 8) / 1e9),
-                   "step": "weights and Adam state reset to the same seed before every step"},
+        "config": workload_config(wl),
+        "notes": {"parallelism": f"starts sharded x{world}, weights replicated",
+                  "l2_cache": "inputs larger than L2: per-start L-BFGS-B state %.2f GB per GPU streams "
+                              "through HBM every round (>> 126 MB L2); no explicit flush" %
+                              (S * (256 + (4 * D + D * 21 + 500) * 8) / 1e9),
+                  "step": "weights and Adam state reset to the same seed before every step",
+                  "argmax_path": "fused persistent kernel" if agg["fused"] else "lock-step rounds"},
         "bo_iterations_per_sec": 1e3 / ms_per_step,
         "phases": {"fit_ms": timers["fit_ms"] / K, "argmax_ms": timers["argmax_ms"] / K,
                    "lbfgsb_rounds": agg["rounds"] / K, "evals_per_step_per_gpu": agg["evals"] / K,
@@ -439,10 +486,13 @@ def run_ours(args, wl, rank, local_rank, world):
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / e2e_steps,
                 "steps": e2e_steps, "api": "MaximizableSequential.fit + .argmax (numpy in/out)"},
         # per step: reset (2 copies are not kernels) + fit + (pack + predict) + pack + L-BFGS-B init
-        # + per round (K2 + stepper) + results + select_best
-        "gpu_launches": int(K * 7 + 2 * agg["rounds"]),
+        # + per round (K2 + stepper) + results + select_best; fused: fit + pack + predict + 1 + select
+        "gpu_launches": int(K * 5 + agg["rounds"]) if agg["fused"] else int(K * 7 + 2 * agg["rounds"]),
         "clocks": clocks,
+        "strong": strong,
     }
+    if cfg4 is not None:
+        line["cfg4"] = cfg4
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(wl, X, z, perms, w0)
     print(json.dumps(line), flush=True)
@@ -465,11 +515,12 @@ def cpu_baseline(wl, X, z, perms, w0):
             "host_cores_available": os.cpu_count()}
 
 
-def run_cfg4(args, rank, local_rank, world):
+def cfg4_measure(rank, local_rank, world, steps, warm):
     """BASELINE.json configs[3]: 4,096 independent BO problems (seeds of 6-D Hartmann) trained
     and maximised concurrently, problems sharded over the ranks with no collective.  A step =
     one BO iteration of EVERY problem (fit 125 epochs on 500 observations + 1,024-sample
-    screening + 5-start L-BFGS-B each, the plugin defaults)."""
+    screening + 5-start L-BFGS-B each, the plugin defaults), timed on the host clock around the
+    public API (numpy in/out).  Returns the record on rank 0, None elsewhere."""
     import torch
     import torch.distributed as dist
     from bore_b200 import BatchedMaximizableSequential, Dense, problem_shard
@@ -477,7 +528,7 @@ def run_cfg4(args, rank, local_rank, world):
     total, N, D, E, B, K, P = 4096, 500, 6, 125, 64, 5, 1024
     lo_p, hi_p = problem_shard(total, rank, world)
     M = hi_p - lo_p
-    dims, acts = [6, 32, 32, 1], ["relu", "relu", "sigmoid"]
+    dims = [6, 32, 32, 1]
     rs = np.random.RandomState(100 + rank)
     X = rs.uniform(size=(M, N, D))
     y = np.stack([hartmann6(X[p]) for p in range(M)])
@@ -491,49 +542,63 @@ def run_cfg4(args, rank, local_rank, world):
     model.set_weights([glorot_init(dims, 1000 + lo_p + p) for p in range(M)])
     params = model._net.params_tensor()
     w0d = params.clone()
+    phase = dict(fit=0.0, argmax=0.0)
 
-    def step():
+    def step(record=False):
         params.copy_(w0d)                 # the same work every step: same init, fresh optimizer
         model._net.reset_optimizer()
+        t0 = time.perf_counter()
         model.fit(X, z, batch_size=B, epochs=E, permutations=perms)
+        if record:
+            torch.cuda.synchronize()
+        t1 = time.perf_counter()
         res = model.argmax([(0.0, 1.0)] * D, num_starts=K, num_samples=P, X_init=X_init)
+        t2 = time.perf_counter()
+        if record:
+            phase["fit"] += t1 - t0; phase["argmax"] += t2 - t1
         return model._last_stats["evals"], int(res.found.sum())
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-    for _ in range(max(1, min(args.warmup, 2))):
+    for _ in range(warm):
         step()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
     t0 = time.perf_counter()
     evals = 0
-    for _ in range(args.steps):
+    for _ in range(steps):
         e, found = step()
         evals += e
     barrier()
     dt = time.perf_counter() - t0
     clocks = sampler.stop()
+    step(record=True)                     # one extra step with a sync between the phases
     t = torch.tensor([dt, float(evals)], dtype=torch.float64, device="cuda")
     if world > 1:
         a = t.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
         b = t.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
         dt, evals = a[0].item(), b[1].item()
     if rank != 0:
-        return
-    K_ = args.steps
-    line = {"metric": "bo_iterations_per_sec", "value": total * K_ / dt, "unit": "BO iterations/s",
-            "n_gpus": world, "steps": K_, "warmup": max(1, min(args.warmup, 2)),
-            "ms_per_step": 1e3 * dt / K_, "higher_is_better": True, "scaling": "strong",
+        return None
+    return {"metric": "bo_iterations_per_sec", "value": total * steps / dt, "unit": "BO iterations/s",
+            "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32 MLP / f64 L-BFGS-B", "data": "synthetic",
             "config": {"workload": "4096 independent Hartmann-6 BO problems / Dense32x2-ReLU+sigmoid / "
-                                   "N=500, 125 epochs, 1024 samples -> 5 starts each",
-                       "parallelism": f"problems sharded x{world}, no collective",
-                       "timing": "host clock around the public API (numpy in/out), i.e. end to end"},
+                                   "N=500, 125 epochs, 1024 samples -> 5 starts each"},
+            "notes": {"parallelism": f"problems sharded x{world}, no collective",
+                      "timing": "host clock around the public API (numpy in/out), i.e. end to end"},
+            "phases_ms_rank0": {"fit": 1e3 * phase["fit"], "argmax": 1e3 * phase["argmax"]},
             "evals_per_sec": evals / dt, "found_last_step": found, "clocks": clocks}
-    print(json.dumps(line), flush=True)
+
+
+def run_cfg4(args, rank, local_rank, world):
+    line = cfg4_measure(rank, local_rank, world, steps=args.steps, warm=max(1, min(args.warmup, 2)))
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 def main():
@@ -544,6 +609,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS) + ["cfg4"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cfg4", action="store_true", help="skip the short cfg 4 sub-record")
     args = ap.parse_args()
     from bore_b200 import distributed as bd
     rank, local_rank, world = bd.env_world()

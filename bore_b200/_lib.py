@@ -41,6 +41,8 @@ SIGNATURES = {
     "bore_mlp_evaluate": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp, vp]),
     "bore_mlp_set_regularizers": (C.c_int, [vp, vp, vp]),
     "bore_lbfgsb_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "bore_lbfgsb_minimize_workspace_bytes": (C.c_size_t, [vp, C.c_int, C.c_int]),
+    "bore_lbfgsb_set_mode": (C.c_int, [C.c_int]),
     "bore_lbfgsb_minimize": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_int,
                                        C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
                                        vp, C.c_size_t, vp, vp, vp, vp, vp, vp,

@@ -37,6 +37,7 @@
 #include <cmath>
 
 #include "common.cuh"
+#include "lbfgsb_fused.h"
 #include "lbfgsb_types.h"
 
 namespace lbw {  // warp-collective variant, run-time history size m
@@ -494,6 +495,7 @@ struct LbProfile {
   std::vector<cudaEvent_t> pool;
   double k2_ms = 0, step_ms = 0, bytes = 0, evals = 0;
   int rounds = 0, k2_launches = 0, step_launches = 0;
+  int fused = 0, grid = 0, block = 0;
   cudaEvent_t get(size_t i) {
     while (pool.size() <= i) {
       cudaEvent_t e;
@@ -546,9 +548,10 @@ int plan_step(int S, int n, int m, int sm_count, StepLaunch &L) {
   return 0;
 }
 
-int setup_params(LbDev &D, const LbLayout &L, char *work, int S, int n, int m, const double *lo_h,
-                 const double *hi_h, double ftol, double gtol, int maxiter, int maxfun, int maxls,
-                 cudaStream_t stream) {
+// SciPy's bounds -> (l, u, nbd) (_lbfgsb_py.py:367-380), uploaded to lo_d / hi_d / nbd_d; fills P
+int setup_problem(LbParams &P, double *lo_d, double *hi_d, int *nbd_d, int n, int m, const double *lo_h,
+                  const double *hi_h, double ftol, double gtol, int maxiter, int maxfun, int maxls,
+                  cudaStream_t stream) {
   std::vector<double> lo(n), hi(n);
   std::vector<int> nbd(n);
   int cnstnd = 0, boxed = 1;
@@ -562,15 +565,23 @@ int setup_params(LbDev &D, const LbLayout &L, char *work, int S, int n, int m, c
     if (nbd[i] != 2) boxed = 0;
     if (nbd[i] != 0) cnstnd = 1;
   }
-  BORE_CUDA(cudaMemcpyAsync(work + L.lo, lo.data(), n * sizeof(double), cudaMemcpyHostToDevice, stream));
-  BORE_CUDA(cudaMemcpyAsync(work + L.hi, hi.data(), n * sizeof(double), cudaMemcpyHostToDevice, stream));
-  BORE_CUDA(cudaMemcpyAsync(work + L.nbd, nbd.data(), n * sizeof(int), cudaMemcpyHostToDevice, stream));
+  BORE_CUDA(cudaMemcpyAsync(lo_d, lo.data(), n * sizeof(double), cudaMemcpyHostToDevice, stream));
+  BORE_CUDA(cudaMemcpyAsync(hi_d, hi.data(), n * sizeof(double), cudaMemcpyHostToDevice, stream));
+  BORE_CUDA(cudaMemcpyAsync(nbd_d, nbd.data(), n * sizeof(int), cudaMemcpyHostToDevice, stream));
   BORE_CUDA(cudaStreamSynchronize(stream));  // the host vectors die at return
-  D.P.n = n; D.P.m = m; D.P.maxiter = maxiter; D.P.maxfun = maxfun; D.P.maxls = maxls;
-  D.P.cnstnd = cnstnd; D.P.boxed = boxed; D.P.ftol = ftol; D.P.pgtol = gtol;
-  D.P.lo = reinterpret_cast<const double *>(work + L.lo);
-  D.P.hi = reinterpret_cast<const double *>(work + L.hi);
-  D.P.nbd = reinterpret_cast<const int *>(work + L.nbd);
+  P.n = n; P.m = m; P.maxiter = maxiter; P.maxfun = maxfun; P.maxls = maxls;
+  P.cnstnd = cnstnd; P.boxed = boxed; P.ftol = ftol; P.pgtol = gtol;
+  P.lo = lo_d; P.hi = hi_d; P.nbd = nbd_d;
+  return 0;
+}
+
+int setup_params(LbDev &D, const LbLayout &L, char *work, int S, int n, int m, const double *lo_h,
+                 const double *hi_h, double ftol, double gtol, int maxiter, int maxfun, int maxls,
+                 cudaStream_t stream) {
+  if (setup_problem(D.P, reinterpret_cast<double *>(work + L.lo), reinterpret_cast<double *>(work + L.hi),
+                    reinterpret_cast<int *>(work + L.nbd), n, m, lo_h, hi_h, ftol, gtol, maxiter, maxfun,
+                    maxls, stream))
+    return -1;
   D.S = S;
   D.blocks = work + L.blocks;
   D.block_stride = L.block_stride;
@@ -632,6 +643,35 @@ int check_opts(int S, int D, int m, int maxls) {
   return 0;
 }
 
+// BORE_LB_FUSED=0 in the environment sends bore_lbfgsb_minimize through the lock-step rounds
+// (K2 launch + stepper launch per round) instead of the fused persistent kernel: the comparison
+// arm of the tests and of tools/
+// Which path runs a bore_lbfgsb_minimize call.  Measured on B200 (tools/fused_ab.py, cfg 3 net):
+// the fused persistent kernel wins while the starts are few enough that the lock-step rounds run at
+// their launch-latency floor -- 1,024 starts 1.7 vs 8.6 ms, 8,192 starts 23.9 vs 28.6 ms -- and
+// loses at 65,536 (182 vs 130 ms): there the warps of an SM sit at nine different places of a
+// ~100 KB instruction stream (ncu: no_instruction is 45 % of its stall cycles), which the
+// rendezvous of the round kernel avoids.  Hence by default fused up to FUSED_MAX_STARTS starts,
+// rounds above.  g_lb_mode: -1 from the environment (BORE_LB_FUSED = 0 never / 1 default / 2
+// always fused when it fits), 0 default rule, 1 always rounds, 2 always fused.
+constexpr int FUSED_MAX_STARTS = 16384;
+int g_lb_mode = -1;
+int lb_mode() {
+  if (g_lb_mode < 0) {
+    const char *e = getenv("BORE_LB_FUSED");
+    const int v = e ? atoi(e) : 1;
+    g_lb_mode = v == 0 ? 1 : (v == 2 ? 2 : 0);
+  }
+  return g_lb_mode;
+}
+bool use_fused(const bore_mlp *h, int S, int m, int per_model) {
+  const int mode = lb_mode();
+  if (mode == 1) return false;
+  // (batched problems: a few starts per model, the rounds never leave their latency floor)
+  if (mode == 0 && per_model == 0 && S > FUSED_MAX_STARTS) return false;
+  return m <= BORE_LBFGSB_MAXCOR && lbfgsb_fused_fits(h, m) != 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -639,6 +679,19 @@ extern "C" {
 size_t bore_lbfgsb_workspace_bytes(int S, int D, int m) {
   if (S < 1 || D < 1 || m < 1) return 0;
   return EXT_HDR + make_layout(S, D, m).total;
+}
+
+int bore_lbfgsb_set_mode(int mode) {
+  BORE_CHECK(mode >= 0 && mode <= 2, "bore_lbfgsb_set_mode: mode %d (0 default, 1 lock-step rounds, 2 fused)", mode);
+  g_lb_mode = mode;
+  return 0;
+}
+
+size_t bore_lbfgsb_minimize_workspace_bytes(const bore_mlp *h, int S, int m) {
+  if (!h || S < 1 || m < 1) return 0;
+  const int D = h->desc.dims[0];
+  if (use_fused(h, S, m, 0)) return EXT_HDR + lbfgsb_fused_workspace_bytes(D);
+  return bore_lbfgsb_workspace_bytes(S, D, m);
 }
 
 // shared body of bore_lbfgsb_minimize (n_models == 1, per_model == 0: all S starts belong to
@@ -658,6 +711,43 @@ static int minimize_impl(bore_mlp *h, int model, int n_models, int per_model, in
   BORE_CHECK(x_dev && X0_dev && work_dev, "NULL buffer");
   BORE_CUDA(cudaSetDevice(h->device));
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (use_fused(h, S, m, per_model)) {
+    // ---- the whole argmax in one persistent launch (lbfgsb_fused.cu) ----
+    const size_t need = EXT_HDR + lbfgsb_fused_workspace_bytes(n);
+    BORE_CHECK(work_bytes >= need, "lbfgsb workspace too small: %zu < %zu", work_bytes, need);
+    char *work = static_cast<char *>(work_dev) + EXT_HDR;
+    // [queue head, evaluation counter (64 B)] lo | hi | nbd
+    double *lo_d = reinterpret_cast<double *>(work + 64);
+    double *hi_d = lo_d + align_up(n * sizeof(double), 16) / sizeof(double);
+    int *nbd_d = reinterpret_cast<int *>(hi_d + align_up(n * sizeof(double), 16) / sizeof(double));
+    LbParams P;
+    if (setup_problem(P, lo_d, hi_d, nbd_d, n, m, lo_host, hi_host, ftol, gtol, maxiter, maxfun, maxls, stream))
+      return -1;
+    if (g_prof.enabled) cudaEventRecord(g_prof.get(0), stream);
+    long long evals = 0;
+    FusedLaunchInfo info;
+    const int rc = launch_lbfgsb_fused(h, model, n_models, per_model, transform, X0_dev, S, P, work, x_dev,
+                                       fun_dev, nit_dev, nfev_dev, status_dev, task_dev, nullptr, &info, stream);
+    if (rc) return rc;
+    if (g_prof.enabled) cudaEventRecord(g_prof.get(1), stream);
+    BORE_CUDA(cudaMemcpyAsync(&evals, work + 8, sizeof(evals), cudaMemcpyDeviceToHost, stream));
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { bore_set_error("lbfgsb (fused): %s", cudaGetErrorString(e)); return -2; }
+    if (evals_out) *evals_out = evals;
+    if (rounds_out) *rounds_out = 1;
+    if (g_prof.enabled) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, g_prof.get(0), g_prof.get(1));
+      g_prof.k2_ms = 0; g_prof.step_ms = ms; g_prof.rounds = 1;
+      g_prof.k2_launches = 0; g_prof.step_launches = 1;
+      // HBM traffic an ideal implementation needs: start points in, iterates and 5 scalars out
+      g_prof.bytes = (double)S * (16.0 * n + 24.0);
+      g_prof.evals = (double)evals;
+      g_prof.fused = 1; g_prof.grid = info.grid; g_prof.block = info.block;
+    }
+    return 0;
+  }
+  g_prof.fused = 0;
   const LbLayout L = make_layout(S, n, m);
   BORE_CHECK(work_bytes >= EXT_HDR + L.total, "lbfgsb workspace too small: %zu < %zu", work_bytes,
              EXT_HDR + L.total);
@@ -788,12 +878,14 @@ int bore_lbfgsb_profile(int enable) {
   g_prof.enabled = enable != 0;
   return 0;
 }
-// out[0] K2 total ms, out[1] stepper total ms, out[2] rounds (= launches of each kernel),
-// out[3] stepper algorithmic bytes, out[4] K2 point evaluations -- of the last profiled call
+// out[0] K2 total ms, out[1] stepper (or fused kernel) total ms, out[2] rounds (= launches of each
+// kernel), out[3] algorithmic bytes, out[4] point evaluations, out[5] 1 = fused persistent kernel,
+// out[6] / out[7] its grid / block size -- of the last profiled call
 int bore_lbfgsb_last_profile(double *out) {
   BORE_CHECK(out != nullptr, "NULL argument");
   out[0] = g_prof.k2_ms; out[1] = g_prof.step_ms; out[2] = g_prof.rounds;
   out[3] = g_prof.bytes; out[4] = g_prof.evals;
+  out[5] = g_prof.fused; out[6] = g_prof.grid; out[7] = g_prof.block;
   return 0;
 }
 

@@ -97,23 +97,26 @@ typedef double *LbDP;
 typedef int *LbIP;
 
 // ------------------------------------------------------------------ warp collectives
+// (the butterflies are fully unrolled: rolled, the compiler shuffles the register pair of the
+// double through a chain of XOR swaps -- 13 instructions per step instead of 3; the helpers are
+// real functions, so there is one copy of each)
 LB_NI double lb_sum(double v) {
 #if LB_WARP
-  LB_UNROLL1
+#pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
 #endif
   return v;
 }
 LB_NI double lb_max(double v) {
 #if LB_WARP
-  LB_UNROLL1
+#pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
 #endif
   return v;
 }
 LB_NI int lb_isum(int v) {
 #if LB_WARP
-  LB_UNROLL1
+#pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
 #endif
   return v;
@@ -129,7 +132,7 @@ LB_FN int lb_any(int p) {
 struct LbArgMin { double v; int idx; };
 LB_NI LbArgMin lb_argmin(double v, int idx) {
 #if LB_WARP
-  LB_UNROLL1
+#pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     double ov = __shfl_xor_sync(0xffffffffu, v, o);
     int oi = __shfl_xor_sync(0xffffffffu, idx, o);
@@ -164,6 +167,8 @@ struct LbWork {
   LbIP index;                         // [n] free variables first (count nfree), active after
                                       //     (warp variant only; the serial variants mask)
   const int *ftab;                    // formk output map (lb_formk_code), one per CTA, warp variant only
+  int changed;                        // out: the request lb_advance just posted differs from the point
+                                      //      evaluated last (SciPy memoises on x: a repeat is not an nfev)
 };
 
 LB_HD size_t lb_work_doubles(int n, int m) {
@@ -1189,6 +1194,7 @@ LB_FN int lb_advance(const LbParams &P, LbWork &w, LbScal &s, Mem &mem, int stag
   const int n = P.n, m = LB_M(P.m);
   enum { ST_TESTS, ST_ITER, ST_REQUEST, ST_FAIL };
   int st;
+  int restored = 0;  // w.x was reset to the previous iterate (it no longer is the point evaluated last)
 
   if (s.phase == LB_PH_DONE) return 0;
   if (stage != 2) {
@@ -1365,7 +1371,8 @@ LB_FN int lb_advance(const LbParams &P, LbWork &w, LbScal &s, Mem &mem, int stag
         st = ST_FAIL;
       } else {
         LB_SYNC();
-        if (s.stp == 1.0) { LB_FOR(i, n) w.x[i] = w.z[i]; }
+        int chg = restored;
+        if (s.stp == 1.0) { LB_FOR(i, n) { const double xi = w.z[i]; chg |= (w.x[i] != xi); w.x[i] = xi; } }
         else {
           // SciPy's lnsrlb also clamps the trial point into the box, so that rounding in
           // stp*d + xold cannot step outside (scipy/optimize/tests/test_lbfgsb_setulb.py:70-113)
@@ -1374,9 +1381,11 @@ LB_FN int lb_advance(const LbParams &P, LbWork &w, LbScal &s, Mem &mem, int stag
             const int nb = P.nbd[i];
             if (nb == 1 || nb == 2) xi = fmax(xi, P.lo[i]);
             if (nb == 2 || nb == 3) xi = fmin(xi, P.hi[i]);
+            chg |= (w.x[i] != xi);
             w.x[i] = xi;
           }
         }
+        w.changed = lb_any(chg);
         LB_SYNC();
         s.phase = LB_PH_LNSRCH;
         return 1;
@@ -1388,6 +1397,7 @@ LB_FN int lb_advance(const LbParams &P, LbWork &w, LbScal &s, Mem &mem, int stag
     LB_SYNC();
     LB_FOR(i, n) { w.x[i] = w.t[i]; w.g[i] = w.r[i]; }
     s.f = s.fold;
+    restored = 1;
     LB_SYNC();
     if (s.col == 0) {
       s.iter += 1;

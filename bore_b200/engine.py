@@ -261,7 +261,7 @@ class NativeMLP:
         assert D == self.D and X0_dev.dtype == torch.float64 and X0_dev.is_contiguous()
         lo = np.ascontiguousarray(np.broadcast_to(np.asarray(lo, np.float64), (D,)))
         hi = np.ascontiguousarray(np.broadcast_to(np.asarray(hi, np.float64), (D,)))
-        nbytes = self.lib.bore_lbfgsb_workspace_bytes(S, D, m)
+        nbytes = self.lib.bore_lbfgsb_minimize_workspace_bytes(self.h, S, m)
         work = self._workspace(nbytes)
         dev = self._tdev()
         x = torch.empty(S, D, dtype=torch.float64, device=dev)
@@ -336,7 +336,7 @@ class NativeMLP:
         S = M * K
         lo = np.ascontiguousarray(np.broadcast_to(np.asarray(lo, np.float64), (D,)))
         hi = np.ascontiguousarray(np.broadcast_to(np.asarray(hi, np.float64), (D,)))
-        work = self._workspace(self.lib.bore_lbfgsb_workspace_bytes(S, D, m))
+        work = self._workspace(self.lib.bore_lbfgsb_minimize_workspace_bytes(self.h, S, m))
         dev = self._tdev()
         x = torch.empty(M, K, D, dtype=torch.float64, device=dev)
         fun = torch.empty(M, K, dtype=torch.float64, device=dev)

@@ -142,6 +142,17 @@ int bore_mlp_evaluate(bore_mlp *h, int model, const float *X_dev, const float *z
  * NULL) receives the number of lock-step evaluation rounds, *evals_out the total number
  * of K2 point evaluations performed.                                                    */
 size_t bore_lbfgsb_workspace_bytes(int S, int D, int m);
+/* Scratch bore_lbfgsb_minimize / _minimize_multi need for S starts on model handle `h`: a few
+ * hundred bytes when the fused persistent kernel runs the call (weights and >= 2 starts fit in
+ * one SM's shared memory -- every BASELINE.json config), else bore_lbfgsb_workspace_bytes.   */
+size_t bore_lbfgsb_minimize_workspace_bytes(const bore_mlp *h, int S, int m);
+/* How bore_lbfgsb_minimize / _minimize_multi run (process-wide): 0 = default rule -- ONE fused
+ * persistent launch (a warp keeps its start in shared memory and evaluates the MLP itself) when
+ * the model fits and S <= 16,384, lock-step rounds of K2 + stepper launches above; 1 = always
+ * rounds (the path bore_lbfgsb_step exposes); 2 = always fused when the model fits.
+ * BORE_LB_FUSED=0 / 1 / 2 in the environment selects 1 / 0 / 2 at start-up.  Query workspace
+ * sizes after changing it.                                                                  */
+int bore_lbfgsb_set_mode(int mode);
 int bore_lbfgsb_minimize(bore_mlp *h, int model, int transform, const double *X0_dev,
                          int S, const double *lo_host, const double *hi_host, int m,
                          double ftol, double gtol, int maxiter, int maxfun, int maxls,
@@ -152,10 +163,12 @@ int bore_lbfgsb_minimize(bore_mlp *h, int model, int transform, const double *X0
 
 /* Measurement hooks for bench.py: when enabled, bore_lbfgsb_minimize brackets every kernel it
  * launches with CUDA events on `stream`; bore_lbfgsb_last_profile returns, for the last such
- * call, out[0] = K2 total ms, out[1] = stepper total ms, out[2] = rounds (= launches of each
- * kernel), out[3] = stepper algorithmic bytes, out[4] = K2 point evaluations.  */
+ * call, out[0] = K2 total ms, out[1] = stepper (or fused kernel) total ms, out[2] = rounds
+ * (= launches of each kernel), out[3] = algorithmic bytes, out[4] = point
+ * evaluations, out[5] = 1 when the fused persistent kernel ran, out[6] / out[7] = its grid /
+ * block size.                                                                              */
 int bore_lbfgsb_profile(int enable);
-int bore_lbfgsb_last_profile(double *out5);
+int bore_lbfgsb_last_profile(double *out8);
 
 /* L-BFGS-B stepper alone, objective supplied by the caller (reverse communication):
  * used to pin the on-device algorithm against SciPy's setulb request by request, and by
