@@ -248,6 +248,7 @@ constexpr int LB_NPHASE_MAX = 4;
 // barriers.
 struct BlockMem {
   bool loaded = false, is_dirty = false, vec_dirty = false, requested = false;
+  __device__ bool ld_kept() { return false; }  // the state was staged in from HBM: ld must be rebuilt
   int nph = 0, cap = LB_NPHASE_MAX;
   uint64_t *bar = nullptr;  // mbarrier of the second piece, and the parity of its current phase
   uint32_t parity = 0;

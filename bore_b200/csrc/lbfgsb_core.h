@@ -96,6 +96,11 @@
 typedef double *LbDP;
 typedef int *LbIP;
 
+// ld = L D^-1 lives in rows m..2m-1, columns 0..m-1 of wn (leading dimension 2m): the (2,1) block
+// of the K matrix, which nothing else touches -- formt's scratch is rows 0..m-1, formk and the
+// factorisations only ever read or write the upper triangle.
+#define LB_LDL(m) (2 * (m))
+
 // ------------------------------------------------------------------ warp collectives
 // (the butterflies are fully unrolled: rolled, the compiler shuffles the register pair of the
 // double through a chain of XOR swaps -- 13 instructions per step instead of 3; the helpers are
@@ -159,7 +164,7 @@ struct LbWork {
   LbDP x, g, z, r, d, t, xp;          // [n]
   LbDP W;                             // [n][LDW]: wy cols 0..m-1, ws cols m..2m-1 (logical order)
   LbDP sy, ss, yy, tinv;              // [m][m] persisted (contiguous, in this order)
-  double *ld;                         // [m][m] derived from sy (lb_prep_ld)
+  double *ld;                         // [m][LB_LDL(m)] derived from sy (lb_prep_ld); inside wn
   double *wn;                         // [2m][2m] upper triangle (also scratch of formt)
   double *rd;                         // [2m] reciprocal diagonal of the last Cholesky factors
   double *p, *c, *wbp, *v, *q;        // [2m]
@@ -172,7 +177,7 @@ struct LbWork {
 };
 
 LB_HD size_t lb_work_doubles(int n, int m) {
-  return (size_t)LB_PERSIST_DOUBLES(n, m) + 3 * LB_NV(n) + 4 * m * m + 12 * m;
+  return (size_t)LB_PERSIST_DOUBLES(n, m) + 2 * LB_NV(n) + 4 * m * m + 12 * m;
 }
 LB_HD size_t lb_work_ints(int n) { return 2 * (size_t)n; }
 
@@ -184,10 +189,11 @@ LB_FN void lb_carve(LbWork &w, double *dbase, int *ibase, int n, int m) {
   w.t = q; q += nv; w.r = q; q += nv; w.d = q; q += nv; w.z = q; q += nv;
   w.W = q; q += LB_NW(n, m);
   w.sy = q; q += m * m; w.ss = q; q += m * m; w.yy = q; q += m * m; w.tinv = q; q += m * m;
-  w.ld = q;
   q = dbase + LB_PERSIST_DOUBLES(n, m);  // scratch starts behind the (padded) persisted block
-  w.x = q; q += nv; w.g = q; q += nv; w.xp = q; q += nv;
+  w.x = q; q += nv; w.g = q; q += nv;
+  w.xp = w.t;  // the Cauchy breakpoints (t) are dead by the time subsm saves the Cauchy point
   w.wn = q; q += 4 * m * m;
+  w.ld = w.wn + m * LB_LDL(m);
   w.rd = q; q += 2 * m;
   w.p = q; q += 2 * m; w.c = q; q += 2 * m; w.wbp = q; q += 2 * m; w.v = q; q += 2 * m;
   w.q = q; q += 2 * m;
@@ -335,17 +341,17 @@ LB_NI void lb_trsl_n(const double *R, int ld, int n, const double *rd, double *b
 LB_FN void lb_prep_ld(LbWork &w, int m, int col) {
   m = LB_M(m);
   LB_SYNC();
-  LB_FOR(k, col) w.ld[k * m + k] = 1.0 / w.sy[k * m + k];
+  LB_FOR(k, col) w.ld[k * LB_LDL(m) + k] = 1.0 / w.sy[k * m + k];
   LB_SYNC();
 #if LB_WARP
   LB_FOR(p, m * (m + 1) / 2) {
     const int cd = w.ftab[p];
     const int i = LB_PAIR_HI(cd), k = LB_PAIR_LO(cd);
-    if (i < col && k < i) w.ld[i * m + k] = w.sy[i * m + k] * w.ld[k * m + k];
+    if (i < col && k < i) w.ld[i * LB_LDL(m) + k] = w.sy[i * m + k] * w.ld[k * LB_LDL(m) + k];
   }
 #else
   for (int i = 1; i < col; ++i)
-    for (int k = 0; k < i; ++k) w.ld[i * m + k] = w.sy[i * m + k] * w.ld[k * m + k];
+    for (int k = 0; k < i; ++k) w.ld[i * LB_LDL(m) + k] = w.sy[i * m + k] * w.ld[k * LB_LDL(m) + k];
 #endif
   LB_SYNC();
 }
@@ -361,7 +367,7 @@ LB_NI void lb_bmv(const double *ld, const double *tinv, double *q, int m, int co
   LB_FOR(i, col) {
     double a = v[col + i];
     LB_UNROLL_HOT
-    for (int k = 0; k < i; ++k) a += ld[i * m + k] * v[k];
+    for (int k = 0; k < i; ++k) a += ld[i * LB_LDL(m) + k] * v[k];
     q[i] = a;
   }
   LB_SYNC();
@@ -373,9 +379,9 @@ LB_NI void lb_bmv(const double *ld, const double *tinv, double *q, int m, int co
   }
   LB_SYNC();
   LB_FOR(i, col) {
-    double a = -ld[i * m + i] * v[i];
+    double a = -ld[i * LB_LDL(m) + i] * v[i];
     LB_UNROLL_HOT
-    for (int k = i + 1; k < col; ++k) a += ld[k * m + i] * p[col + k];
+    for (int k = i + 1; k < col; ++k) a += ld[k * LB_LDL(m) + i] * p[col + k];
     p[i] = a;
   }
   LB_SYNC();
@@ -397,7 +403,7 @@ LB_FN int lb_formt(LbWork &w, int m, int col, double theta) {
     if (j < col) {
       double a = theta * w.ss[i * m + j];
       LB_UNROLL_HOT
-      for (int k = 0; k < i; ++k) a += w.ld[i * m + k] * w.sy[j * m + k];
+      for (int k = 0; k < i; ++k) a += w.ld[i * LB_LDL(m) + k] * w.sy[j * m + k];
       T[i * m + j] = a;
     }
   }
@@ -440,7 +446,7 @@ LB_FN int lb_formt(LbWork &w, int m, int col, double theta) {
   for (int i = 0; i < col; ++i)
     for (int j = i; j < col; ++j) {
       double a = theta * w.ss[i * m + j];
-      for (int k = 0; k < i; ++k) a += w.ld[i * m + k] * w.sy[j * m + k];
+      for (int k = 0; k < i; ++k) a += w.ld[i * LB_LDL(m) + k] * w.sy[j * m + k];
       T[i * m + j] = a;
     }
   if (lb_chol(T, m, col, w.rd)) return -3;
@@ -1177,6 +1183,8 @@ LB_FN void lb_matupd(const LbParams &P, LbWork &w, LbScal &s, double rr, double 
 // minimisation | line-search set-up): the device kernel re-aligns the warps of a CTA there so
 // that they fetch the same instructions at the same time.
 struct LbNoMem {
+  // ld (derived from sy) survives between steps when the state never leaves fast memory
+  LB_FN bool ld_kept() { return true; }
   LB_FN void load() {}
   LB_FN void dirty() {}
   LB_FN void dirty_vec() {}
@@ -1195,6 +1203,7 @@ LB_FN int lb_advance(const LbParams &P, LbWork &w, LbScal &s, Mem &mem, int stag
   enum { ST_TESTS, ST_ITER, ST_REQUEST, ST_FAIL };
   int st;
   int restored = 0;  // w.x was reset to the previous iterate (it no longer is the point evaluated last)
+  int ld_fresh = 0;  // w.ld matches w.sy (built in this call)
 
   if (s.phase == LB_PH_DONE) return 0;
   if (stage != 2) {
@@ -1277,6 +1286,7 @@ LB_FN int lb_advance(const LbParams &P, LbWork &w, LbScal &s, Mem &mem, int stag
         mem.dirty();
         lb_matupd(P, w, s, rr, dr);
         if (lb_formt(w, m, s.col, s.theta)) lb_reset_memory(s);
+        ld_fresh = 1;
       }
       st = ST_ITER;
     }
@@ -1284,6 +1294,10 @@ LB_FN int lb_advance(const LbParams &P, LbWork &w, LbScal &s, Mem &mem, int stag
     if (st == ST_ITER) {
       // ---- new iteration (label 222): search direction ----
       mem.dirty_vec();
+      // ld = L D^-1 is not part of the persisted state: rebuild it unless formt just did, or the
+      // state has been in fast memory all along
+      if (!ld_fresh && !mem.ld_kept() && s.col > 0) lb_prep_ld(w, m, s.col);
+      ld_fresh = 1;
       int nfree = n;
       LB_UNROLL1
       for (;;) {

@@ -349,17 +349,18 @@ __device__ __forceinline__ float fused_eval_any(const FusedHeader *H, const floa
   }
 }
 
-// per-warp workspace: doubles, then ints (see carve below); the K-matrix scratch wn doubles as the
-// activation strips of the MLP
-__host__ __device__ inline size_t fused_scratch_doubles(int m, int strip_floats) {
-  const size_t wn = 4 * (size_t)m * m;
-  const size_t st = ((size_t)strip_floats + 1) / 2;
-  return ((wn > st ? wn : st) + 1) & ~(size_t)1;
+// per-warp workspace: doubles, then ints (see carve below).  The MLP's activation strips alias
+// the FIRST half of the K-matrix scratch wn (rows 0..m-1: formt / formk scratch, dead while the
+// MLP runs) and, if they are larger, extra space in front of it; the second half holds ld.
+__host__ __device__ inline size_t fused_strip_doubles(int m, int strip_floats) {
+  const size_t half = 2 * (size_t)m * m;
+  const size_t st = (((size_t)strip_floats + 1) / 2 + 1) & ~(size_t)1;
+  return st > half ? st : half;  // doubles from the start of the strips to the middle of wn
 }
 __host__ __device__ inline size_t fused_warp_bytes(int n, int m, int strip_floats) {
   const size_t nv = LB_NV(n);
-  const size_t d = 6 * nv + LB_NW(n, m) + ((5 * (size_t)m * m + 1) & ~(size_t)1) +
-                   fused_scratch_doubles(m, strip_floats) + 12 * (size_t)m;
+  const size_t d = 6 * nv + LB_NW(n, m) + ((4 * (size_t)m * m + 1) & ~(size_t)1) +
+                   fused_strip_doubles(m, strip_floats) + 2 * (size_t)m * m + 12 * (size_t)m;
   return f_align(d * sizeof(double) + 2 * (size_t)n * sizeof(int), 16);
 }
 
@@ -371,11 +372,12 @@ __device__ __forceinline__ float *fused_carve(Work &w, unsigned char *base, int 
   w.xp = w.t;  // the Cauchy breakpoints (t) are dead when subsm saves the Cauchy point
   w.W = q; q += LB_NW(n, m);
   w.sy = q; q += m * m; w.ss = q; q += m * m; w.yy = q; q += m * m; w.tinv = q; q += m * m;
-  w.ld = q; q += m * m;
-  if ((5 * m * m) & 1) ++q;  // the scratch starts 16-byte aligned (float4 loads of the strips)
-  w.wn = q;
+  if ((4 * m * m) & 1) ++q;  // the scratch starts 16-byte aligned (float4 loads of the strips)
   float *strip = reinterpret_cast<float *>(q);
-  q += fused_scratch_doubles(m, strip_floats);
+  q += fused_strip_doubles(m, strip_floats);  // -> the middle of wn
+  w.wn = q - 2 * m * m;
+  w.ld = q;                                   // == w.wn + m * LB_LDL(m)
+  q += 2 * m * m;
   w.rd = q; q += 2 * m;
   w.p = q; q += 2 * m; w.c = q; q += 2 * m; w.wbp = q; q += 2 * m; w.v = q; q += 2 * m; w.q = q; q += 2 * m;
   int *ib = reinterpret_cast<int *>(q);

@@ -62,12 +62,14 @@ struct LbScal {
 };
 
 #define LB_LDW(m) (2 * (m) + 1)
-// persisted small matrices per start: sy ss yy tinv ld, each [m][m] (ld = L D^-1 is derived
-// from sy, but keeping it costs 6 % more block bytes and saves recomputing it every step)
-#define LB_NPERSIST_MM 5
+// persisted small matrices per start: sy ss yy tinv, each [m][m].  ld = L D^-1 is derived from
+// sy (lb_prep_ld, ~70 instructions): it is rebuilt whenever a start's state is staged back into
+// fast memory for a new iteration and lives in the otherwise unused (2,1) block of the K-matrix
+// scratch wn -- 800 bytes per start that buy a twelfth resident warp per SM at n = 50.
+#define LB_NPERSIST_MM 4
 // A start's persisted block, in this order in HBM *and* at the head of its workspace, so that
 // staging it in or out is ONE linear (bulk) copy:
-//   scalars (LbScal, LB_SCAL_DOUBLES doubles) | t r d z (4 x LB_NV) | W (LB_NW) | sy ss yy tinv ld
+//   scalars (LbScal, LB_SCAL_DOUBLES doubles) | t r d z (4 x LB_NV) | W (LB_NW) | sy ss yy tinv
 // Vector and W extents are rounded up to even counts: every piece starts 16-byte aligned.
 #define LB_SCAL_DOUBLES 32
 #define LB_NV(n) (((n) + 1) & ~1)
