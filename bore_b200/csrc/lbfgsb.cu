@@ -497,6 +497,7 @@ struct LbProfile {
   double k2_ms = 0, step_ms = 0, bytes = 0, evals = 0;
   int rounds = 0, k2_launches = 0, step_launches = 0;
   int fused = 0, grid = 0, block = 0;
+  double tail_ms = 0;
   cudaEvent_t get(size_t i) {
     while (pool.size() <= i) {
       cudaEvent_t e;
@@ -780,6 +781,21 @@ static int minimize_impl(bore_mlp *h, int model, int n_models, int per_model, in
   BORE_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
   BORE_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
   int round = 0, rc = 0;
+  // Tail handover: once few starts are still running, a lock-step round costs its launch-latency
+  // floor (~93 us for K2 + stepper) whatever it does; the remaining starts are then finished by
+  // the fused persistent kernel in resume mode (state blocks in, state blocks out) -- one launch in
+  // which every start advances at the latency of its own steps.  BORE_LB_HANDOVER = the active
+  // count at which to switch (0 = never).
+  int handover = 0, handover_max = 0;
+  if (per_model == 0 && lb_mode() != 1 && m <= BORE_LBFGSB_MAXCOR && lbfgsb_fused_fits(h, m)) {
+    static int hmax = -1;
+    if (hmax < 0) {
+      const char *e = getenv("BORE_LB_HANDOVER");
+      hmax = e ? atoi(e) : 4096;
+      if (hmax < 0) hmax = 0;
+    }
+    handover_max = hmax;
+  }
   bool have_prev = false;
   int slot = 0;
   const long long max_rounds = (long long)maxfun + (long long)maxls + 8;
@@ -806,10 +822,25 @@ static int minimize_impl(bore_mlp *h, int model, int n_models, int per_model, in
       cudaError_t e = cudaEventSynchronize(ev[slot ^ 1]);
       if (e != cudaSuccess) { bore_set_error("lbfgsb: %s", cudaGetErrorString(e)); rc = -2; break; }
       if (cnt_host[slot ^ 1] == 0) break;
+      if (handover_max > 0 && cnt_host[slot ^ 1] <= handover_max) { handover = cnt_host[slot ^ 1]; break; }
     }
     have_prev = true;
     slot ^= 1;
     if (round > max_rounds) { bore_set_error("lbfgsb: exceeded %lld rounds", max_rounds); rc = -3; break; }
+  }
+  float tail_ms = 0.f;
+  if (!rc && handover > 0) {
+    FusedResume R;
+    R.list = D.lists + (size_t)(round & 1) * S;
+    R.count = D.cnt + round % 3;
+    R.blocks = D.blocks;
+    R.block_stride = D.block_stride;
+    R.qhead = D.work + 3;
+    R.evals = D.evals;
+    if (g_prof.enabled) cudaEventRecord(g_prof.get(3 * (size_t)round), stream);
+    rc = launch_lbfgsb_fused(h, model, 1, 0, transform, nullptr, handover, D.P, work, D.xreq, nullptr, nullptr,
+                             nullptr, nullptr, nullptr, nullptr, nullptr, stream, &R);
+    if (g_prof.enabled) cudaEventRecord(g_prof.get(3 * (size_t)round + 1), stream);
   }
   if (!rc) {
     lbfgsb_results_kernel<<<std::min((S + 127) / 128, 1024), 128, 0, stream>>>(
@@ -832,6 +863,11 @@ static int minimize_impl(bore_mlp *h, int model, int n_models, int per_model, in
         g_prof.k2_ms += a;
         g_prof.step_ms += b;
       }
+      if (handover > 0) {  // the fused tail counts as stepper time (one more launch)
+        cudaEventElapsedTime(&tail_ms, g_prof.get(3 * (size_t)round), g_prof.get(3 * (size_t)round + 1));
+        g_prof.step_ms += tail_ms;
+      }
+      g_prof.tail_ms = tail_ms;
       g_prof.rounds = round;
       g_prof.k2_launches = g_prof.step_launches = round;
       g_prof.bytes = (double)bytes;

@@ -69,6 +69,7 @@ template <> struct Core<0> {
   static __device__ __forceinline__ void init_state(const LbParams &P, Work &w, LbScal &s) {
     lbf::lb_init_state(P, w, s);
   }
+  static __device__ __forceinline__ void prep_ld(Work &w, int m, int col) { lbf::lb_prep_ld(w, m, col); }
   using NoMem = lbf::LbNoMem;
 };
 template <> struct Core<10> {
@@ -80,6 +81,7 @@ template <> struct Core<10> {
   static __device__ __forceinline__ void init_state(const LbParams &P, Work &w, LbScal &s) {
     lbf10::lb_init_state(P, w, s);
   }
+  static __device__ __forceinline__ void prep_ld(Work &w, int m, int col) { lbf10::lb_prep_ld(w, m, col); }
   using NoMem = lbf10::LbNoMem;
 };
 
@@ -143,6 +145,12 @@ struct FusedArgs {
   int *qhead;                 // queue head: next unclaimed start (one model) / model (batched)
   unsigned long long *evals;  // evaluations performed
   size_t warp_bytes;          // shared memory per warp
+  // Resume mode (the tail of a lock-step run, lbfgsb.cu): instead of x0, a start comes with its
+  // persisted state block and a pending request; results go back into the block.
+  const int *resume_list;     // [*resume_count] start ids, or NULL
+  const int *resume_count;
+  char *blocks;               // persisted blocks (layout of lbfgsb_types.h), stride block_stride
+  size_t block_stride;
   FusedPlan plan;
 };
 
@@ -225,9 +233,12 @@ __device__ __noinline__ float fused_eval(const FusedHeader *H, const float *__re
     float *Hn = strip + pl.strip[l + 1];
     if (j0 < WIDTH) {
       const float *W = wsm + pl.w[l] + j0;
-      float acc0[T], acc1[T];
+      // ONE accumulator per output, k ascending: the summation order of K2's tile_gemm, so that
+      // this evaluation is bit-identical to mlp_eval_kernel's (a start may change hands between the
+      // two in mid line search, lbfgsb.cu; mixed roundings would bias its sufficient-decrease tests)
+      float acc[T];
 #pragma unroll
-      for (int t = 0; t < T; ++t) { acc0[t] = 0.f; acc1[t] = 0.f; }
+      for (int t = 0; t < T; ++t) acc[t] = 0.f;
 #pragma unroll 2
       for (int k = 0; k < in4; k += 4) {
         const float4 x4 = *reinterpret_cast<const float4 *>(A + k);
@@ -236,19 +247,16 @@ __device__ __noinline__ float fused_eval(const FusedHeader *H, const float *__re
         W += 4 * LD;
 #pragma unroll
         for (int t = 0; t < T; ++t) {
-          acc0[t] = fmaf(x4.x, w0.v[t], acc0[t]);
-          acc1[t] = fmaf(x4.y, w1.v[t], acc1[t]);
-        }
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-          acc0[t] = fmaf(x4.z, w2.v[t], acc0[t]);
-          acc1[t] = fmaf(x4.w, w3.v[t], acc1[t]);
+          acc[t] = fmaf(x4.x, w0.v[t], acc[t]);
+          acc[t] = fmaf(x4.y, w1.v[t], acc[t]);
+          acc[t] = fmaf(x4.z, w2.v[t], acc[t]);
+          acc[t] = fmaf(x4.w, w3.v[t], acc[t]);
         }
       }
       FVec<T> bv, hv;
       bv.load(wsm + pl.b[l] + j0);
 #pragma unroll
-      for (int t = 0; t < T; ++t) hv.v[t] = f_act_fwd(a, acc0[t] + acc1[t] + bv.v[t]);
+      for (int t = 0; t < T; ++t) hv.v[t] = f_act_fwd(a, acc[t] + bv.v[t]);
       hv.store(Hn + j0);  // pad units: zero weights and bias -> act(0), multiplied by zero rows later
     }
     __syncwarp();
@@ -256,11 +264,16 @@ __device__ __noinline__ float fused_eval(const FusedHeader *H, const float *__re
   // ---- final Dense(1) ----
   float *HL = strip + pl.strip[G];
   const float *wl = wsm + pl.wl;
+  // (K2's association: UG = 16 (8 for nets no wider than 32) partial sums over k = ug, ug + UG, ...,
+  // combined by an xor butterfly; both half-warps compute the same value)
   float up = 0.f;
+  {
+    const int UG = WIDTH > 32 ? 16 : 8;
 #pragma unroll 1
-  for (int k = lane; k < pl.wl_len; k += 32) up = fmaf(HL[k], wl[k], up);
+    for (int k = lane & (UG - 1); k < pl.wl_len; k += UG) up = fmaf(HL[k], wl[k], up);  // (pad terms are +0)
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) up += __shfl_xor_sync(0xffffffffu, up, o);
+    for (int o = 1; o < UG; o <<= 1) up += __shfl_xor_sync(0xffffffffu, up, o);
+  }
   const int act_last = pl.act[G];
   const float u = f_act_fwd(act_last, up + H->b_last);
   const float v = -u;  // the mixin minimises transform(-u) (bore/mixins.py:20)
@@ -302,7 +315,7 @@ __device__ __noinline__ float fused_eval(const FusedHeader *H, const float *__re
       const bool va = ia < in, vb = ib < in;
       const bool two = i0 + 32 < in;  // (warp-uniform) the second row block exists
       const float *ra = W + (va ? ia : 0) * LD, *rb = W + (vb ? ib : 0) * LD;
-      float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+      float a0 = 0.f, b0 = 0.f;  // one accumulator per unit, j ascending (K2's order)
       if (two) {
 #pragma unroll 2
         for (int j = 0; j < out4; j += 4) {
@@ -310,9 +323,9 @@ __device__ __noinline__ float fused_eval(const FusedHeader *H, const float *__re
           const float4 wa = *reinterpret_cast<const float4 *>(ra + j);
           const float4 wb = *reinterpret_cast<const float4 *>(rb + j);
           a0 = fmaf(d4.x, wa.x, a0); b0 = fmaf(d4.x, wb.x, b0);
-          a1 = fmaf(d4.y, wa.y, a1); b1 = fmaf(d4.y, wb.y, b1);
+          a0 = fmaf(d4.y, wa.y, a0); b0 = fmaf(d4.y, wb.y, b0);
           a0 = fmaf(d4.z, wa.z, a0); b0 = fmaf(d4.z, wb.z, b0);
-          a1 = fmaf(d4.w, wa.w, a1); b1 = fmaf(d4.w, wb.w, b1);
+          a0 = fmaf(d4.w, wa.w, a0); b0 = fmaf(d4.w, wb.w, b0);
         }
       } else {
 #pragma unroll 2
@@ -320,18 +333,18 @@ __device__ __noinline__ float fused_eval(const FusedHeader *H, const float *__re
           const float4 d4 = *reinterpret_cast<const float4 *>(Dl + j);
           const float4 wa = *reinterpret_cast<const float4 *>(ra + j);
           a0 = fmaf(d4.x, wa.x, a0);
-          a1 = fmaf(d4.y, wa.y, a1);
+          a0 = fmaf(d4.y, wa.y, a0);
           a0 = fmaf(d4.z, wa.z, a0);
-          a1 = fmaf(d4.w, wa.w, a1);
+          a0 = fmaf(d4.w, wa.w, a0);
         }
       }
       if (l > 0) {
         // in place: every lane reads and writes only its own units, the j loop reads the strip above
-        if (va) Hin[ia] = (a0 + a1) * f_act_bwd(a, Hin[ia]);
-        if (vb) Hin[ib] = (b0 + b1) * f_act_bwd(a, Hin[ib]);
+        if (va) Hin[ia] = a0 * f_act_bwd(a, Hin[ia]);
+        if (vb) Hin[ib] = b0 * f_act_bwd(a, Hin[ib]);
       } else {
-        if (va) g[ia] = (double)(a0 + a1);
-        if (vb) g[ib] = (double)(b0 + b1);
+        if (va) g[ia] = (double)a0;
+        if (vb) g[ib] = (double)b0;
       }
     }
     __syncwarp();
@@ -472,6 +485,8 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) lbfgsb_fused_kernel(c
     __syncthreads();
 
     int k_local = wib;  // batched mode: this warp's next start of the model
+    const int n_items = A.resume_list ? *A.resume_count : A.S;
+    bool resumed_first = false;
     int sid = -1;
     bool have = false;
     int stage = aligned ? 1 : 0;
@@ -488,9 +503,33 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) lbfgsb_fused_kernel(c
           int v = 0;
           if (lane == 0) v = atomicAdd(A.qhead, 1);
           v = __shfl_sync(0xffffffffu, v, 0);
-          sid = v < A.S ? v : -1;
+          sid = v < n_items ? v : -1;
         }
-        if (sid >= 0) {
+        if (sid >= 0 && A.resume_list) {
+          // ---- resume: the start's persisted block (scalars | t r d z | W | sy ss yy tinv) and
+          //      its pending request; the evaluation that follows was counted when it was posted
+          sid = A.resume_list[sid];
+          const double *blk = reinterpret_cast<const double *>(A.blocks + A.block_stride * sid);
+          s = *reinterpret_cast<const LbScal *>(blk);
+          const double *src = blk + LB_SCAL_DOUBLES;
+          const int nv = LB_NV(n);
+#pragma unroll 1
+          for (int i = lane; i < n; i += 32) {
+            w.t[i] = src[i]; w.r[i] = src[nv + i]; w.d[i] = src[2 * nv + i]; w.z[i] = src[3 * nv + i];
+            w.x[i] = A.x[(size_t)sid * n + i];
+            const int nb = s_nbd[i];
+            w.iwhere[i] = nb == 0 ? -1 : ((nb == 2 && s_hi[i] - s_lo[i] <= 0.0) ? 3 : 0);
+          }
+          src += 4 * nv;
+          const int nmat = LB_NW(n, m) + 4 * m * m;  // W and the four matrices are contiguous on both sides
+#pragma unroll 1
+          for (int i = lane; i < nmat; i += 32) w.W[i] = src[i];
+          __syncwarp();
+          if (s.col > 0) Core<MC>::prep_ld(w, m, s.col);
+          have = true;
+          fresh = true;
+          resumed_first = true;
+        } else if (sid >= 0) {
           const double *x0 = A.X0 + (size_t)sid * n;
 #pragma unroll 1
           for (int i = lane; i < n; i += 32) w.x[i] = x0[i];
@@ -515,12 +554,15 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) lbfgsb_fused_kernel(c
           if (stage == 2) stage = 1;
           if (r == 1) {
             s.f = (double)fused_eval_any(H, wsm, strip, w.x, w.g);
-            my_evals += 1;
+            if (!resumed_first) my_evals += 1;
+            resumed_first = false;
           } else {
             // ---- terminated: final iterate and counters ----
             double *xo = A.x + (size_t)sid * n;
 #pragma unroll 1
             for (int i = lane; i < n; i += 32) xo[i] = w.x[i];
+            if (lane == 0 && A.resume_list)
+              *reinterpret_cast<LbScal *>(A.blocks + A.block_stride * sid) = s;  // read by the results kernel
             if (lane == 0) {
               if (A.fun) A.fun[sid] = s.f;
               if (A.nit) A.nit[sid] = s.nit;
@@ -594,7 +636,8 @@ int lbfgsb_fused_fits(const bore_mlp *h, int m) {
 int launch_lbfgsb_fused(const bore_mlp *h, int model0, int n_models, int per_model, int transform,
                         const double *X0_dev, int S, const LbParams &P_dev, void *work_dev,
                         double *x_dev, double *fun_dev, int *nit_dev, int *nfev_dev, int *status_dev,
-                        int *task_dev, long long *evals_out, FusedLaunchInfo *info, cudaStream_t stream) {
+                        int *task_dev, long long *evals_out, FusedLaunchInfo *info, cudaStream_t stream,
+                        const FusedResume *resume) {
   const int n = h->desc.dims[0], m = P_dev.m;
   FusedArgs A;
   make_fused_plan(h->desc, A.plan);
@@ -618,6 +661,13 @@ int launch_lbfgsb_fused(const bore_mlp *h, int model0, int n_models, int per_mod
   }
   A.qhead = reinterpret_cast<int *>(work_dev);
   A.evals = reinterpret_cast<unsigned long long *>(static_cast<char *>(work_dev) + 8);
+  A.resume_list = nullptr; A.resume_count = nullptr; A.blocks = nullptr; A.block_stride = 0;
+  if (resume) {
+    // S = an upper bound of the number of starts still running; the kernel reads the exact count
+    A.resume_list = resume->list; A.resume_count = resume->count;
+    A.blocks = resume->blocks; A.block_stride = resume->block_stride;
+    A.qhead = resume->qhead; A.evals = resume->evals;
+  }
   A.warp_bytes = fused_warp_bytes(n, m, A.plan.strip_total);
   const size_t fixed = fused_header_bytes(n) + f_align((size_t)A.plan.total * sizeof(float), 16);
   const size_t max_block = 227 * 1024, max_sm = 228 * 1024;
@@ -646,7 +696,8 @@ int launch_lbfgsb_fused(const bore_mlp *h, int model0, int n_models, int per_mod
     grid = std::min(h->sm_count, (S + wpb - 1) / wpb);
   }
   const size_t smem = fixed + wpb * A.warp_bytes;
-  BORE_CUDA(cudaMemsetAsync(work_dev, 0, 16, stream));
+  if (resume) BORE_CUDA(cudaMemsetAsync(resume->qhead, 0, sizeof(int), stream));
+  else BORE_CUDA(cudaMemsetAsync(work_dev, 0, 16, stream));
   const int rc = m == 10 ? launch_fused_mc<10>(A, grid, wpb * 32, smem, stream)
                          : launch_fused_mc<0>(A, grid, wpb * 32, smem, stream);
   if (rc) return rc;

@@ -16,7 +16,7 @@ net = NativeMLP(wl["dims"], wl["acts"])
 net.set_weights(bench.glorot_init(wl["dims"], 0))
 net.fit(X, z, wl["epochs"], wl["batch"], perms)
 X0d = torch.from_numpy(np.random.RandomState(1).uniform(size=(S, wl["dims"][0]))).cuda()
-_lib.check(lib.bore_lbfgsb_set_mode({0: 2, 1: 1}[mode]))
+_lib.check(lib.bore_lbfgsb_set_mode({0: 2, 1: 1, 2: 0}[mode]))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ts = []
 for _ in range(reps):
@@ -25,4 +25,8 @@ for _ in range(reps):
     e1.record(); torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
 print(cfg, S, "mode", mode, "env", {k: v for k, v in os.environ.items() if k.startswith("BORE_")}, "ms", [round(t, 2) for t in ts],
-      "evals", r["evals"], "nit", float(r["nit"].float().mean()), "best", float(r["fun"].min()))
+      "evals", r["evals"], "nfev_sum", int(r["nfev"].sum()), "nit", float(r["nit"].float().mean()), "best", float(r["fun"].min()),
+      "status", torch.bincount(r["status"], minlength=3).tolist(), "mean_fun", float(r["fun"].mean()))
+if len(sys.argv) > 5:
+    import numpy as np
+    np.save(sys.argv[5], r["fun"].cpu().numpy())
