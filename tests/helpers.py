@@ -62,3 +62,30 @@ def reference_self_agreement(weights, acts, X0, bounds, transform, tol, ref=None
         ref = am.minimize_starts(weights, acts, X0, bounds, transform=transform)
     alt = am.minimize_starts(permuted_units(weights), acts, X0, bounds, transform=transform)
     return float(np.mean(np.abs(alt["fun"] - ref["fun"]) <= tol)), ref, alt
+
+
+def _minimize_chunk(args):
+    weights, acts, X0, lo, hi, transform, options = args
+    from scipy.optimize import Bounds
+    from threadpoolctl import threadpool_limits
+    from oracle import argmax as am
+    with threadpool_limits(1):  # batch-of-1 matmuls: BLAS threads only add contention
+        return am.minimize_starts(weights, acts, X0, Bounds(lo, hi), options=options, transform=transform)
+
+
+def parallel_minimize_starts(weights, acts, X0, lo, hi, transform, options=dict(maxiter=1000, ftol=1e-9)):
+    """oracle.argmax.minimize_starts with the starts spread over the host cores (one
+    scipy.optimize.minimize per start, as the reference runs them; starts are independent)."""
+    import multiprocessing as mp
+    import os
+    cores = max(1, min(os.cpu_count() or 1, 32))
+    n = X0.shape[1]
+    lo = np.broadcast_to(np.asarray(lo, np.float64), (n,)).copy()
+    hi = np.broadcast_to(np.asarray(hi, np.float64), (n,)).copy()
+    jobs = [(weights, acts, c, lo, hi, transform, options) for c in np.array_split(X0, 2 * cores) if len(c)]
+    if cores == 1:
+        outs = [_minimize_chunk(j) for j in jobs]
+    else:
+        with mp.get_context("fork").Pool(cores) as pool:
+            outs = pool.map(_minimize_chunk, jobs)
+    return {k: np.concatenate([o[k] for o in outs]) for k in outs[0]}

@@ -87,13 +87,16 @@ def oracle_fit():
     hist_ref, adam_ref = km.fit(w_ref, ACTS, X, z, EPOCHS, BATCH, perms)
     w_alt = permuted_units(w0, seed=1)
     hist_alt, _ = km.fit(w_alt, ACTS, X, z, EPOCHS, BATCH, perms)
-    return hist_ref, adam_ref, np.abs(hist_ref - hist_alt)
+    w64 = [w.astype(np.float64) for w in w0]
+    hist64, _ = km.fit(w64, ACTS, X, z, EPOCHS, BATCH, perms, dtype=np.float64)
+    return (hist_ref, adam_ref, np.abs(hist_ref - hist_alt), hist64,
+            np.abs(hist_ref.astype(np.float64) - hist64))
 
 
 @pytest.mark.parametrize("mode", [1, 2])
 def test_full_size_fit_tracks_the_oracle(mode, oracle_fit):
     from bore_b200.engine import NativeMLP
-    hist_ref, adam_ref, self_diff = oracle_fit
+    hist_ref, adam_ref, self_diff, hist64, or32_vs_64 = oracle_fit
     X, z, perms = _problem()
     net = NativeMLP(DIMS, ACTS)
     net.set_fit_mode(mode)
@@ -110,14 +113,16 @@ def test_full_size_fit_tracks_the_oracle(mode, oracle_fit):
     stable = onset - JITTER
     assert stable >= 10, "the oracle itself should be reproducible for the first epochs"
     assert diff[:stable].max() <= LOSS_TOL, (stable, diff[:stable].max())
-    # (2) afterwards: no further from the oracle than a few times what the oracle is from itself
-    #     (same slack on the time axis)
-    run_max = np.maximum.accumulate(self_diff)
-    shifted = np.concatenate([run_max[JITTER:], np.full(JITTER, run_max[-1])])
-    envelope = np.maximum(LOSS_TOL, 4.0 * shifted)
-    assert np.all(diff <= envelope), (diff, envelope)
-    print("full-size fit mode", mode, "stable epochs", stable, "max diff", diff.max(),
-          "oracle self-diff", self_diff.max())
+    # (2) afterwards rounding noise has been amplified through the ReLU kinks and the question is
+    #     which of two fp32 runs is "the" trajectory: judge both against the fp64 oracle -- the CUDA
+    #     kernel may be at most twice as far from it as the fp32 oracle is (same slack on the time
+    #     axis), i.e. it is one more fp32 realisation of the same computation
+    #     (over the whole trajectory: WHEN the amplified noise shows up differs by an epoch or
+    #     three between any two fp32 runs, so an epoch-by-epoch envelope only measures that jitter)
+    d_gpu64 = np.abs(hist.astype(np.float64) - hist64)
+    assert d_gpu64.max() <= 2.0 * or32_vs_64.max(), (d_gpu64.max(), or32_vs_64.max())
+    print("full-size fit mode", mode, "stable epochs", stable, "max diff vs fp32 oracle", diff.max(),
+          "vs fp64 oracle", d_gpu64.max(), "fp32 oracle vs fp64 oracle", or32_vs_64.max())
     assert net.get_adam_state()[2] == adam_ref.t == EPOCHS * (-(-N_OBS // BATCH)) == 992
     assert hist[-1] < hist[0]  # the classifier learned something
 
@@ -181,22 +186,27 @@ def test_full_size_restart_from_converged_points_is_idempotent(trained, full_run
 
 
 def test_full_size_sample_agrees_with_scipy(trained, full_run):
-    from scipy.optimize import Bounds
+    from helpers import parallel_minimize_starts
     net = trained[0]
     X0, _, h = full_run
-    idx = np.random.RandomState(7).choice(S_FULL, 192, replace=False)
+    SAMPLE = 1024  # s.e. of an agreement rate near 0.96: 0.6 points
+    idx = np.random.RandomState(7).choice(S_FULL, SAMPLE, replace=False)
     w = net.get_weights()
-    bounds = Bounds(np.zeros(DIMS[0]), np.ones(DIMS[0]))
-    self_rate, ref, _ = reference_self_agreement(w, ACTS, X0[idx], bounds, TRANSFORM, FUN_TOL)
+    ref = parallel_minimize_starts(w, ACTS, X0[idx], 0.0, 1.0, TRANSFORM)
+    alt = parallel_minimize_starts(permuted_units(w), ACTS, X0[idx], 0.0, 1.0, TRANSFORM)
+    self_rate = float(np.mean(np.abs(alt["fun"] - ref["fun"]) <= FUN_TOL))
+    self_one = float(np.mean(alt["fun"] <= ref["fun"] + FUN_TOL))
     agree = np.abs(h["fun"][idx] - ref["fun"]) <= FUN_TOL
     one_sided = h["fun"][idx] <= ref["fun"] + FUN_TOL
     print("full-size sample: agree", agree.mean(), "one-sided", one_sided.mean(),
-          "reference self-agreement", self_rate)
+          "reference self-agreement", self_rate, "self one-sided", self_one)
     # ReLU objective: the yardstick is how well the reference agrees with itself under an fp32
-    # re-association of the MLP; never below 0.80 outright
-    assert agree.mean() >= min(0.95, self_rate - 0.08)
-    assert agree.mean() >= 0.80
-    assert one_sided.mean() >= 0.85
+    # re-association of the MLP -- within 3 points of it, and never below 0.93
+    assert agree.mean() >= min(0.95, self_rate - 0.03)
+    assert agree.mean() >= 0.93
+    assert one_sided.mean() >= min(0.95, self_one - 0.03)
+    ab_o, ab_r = np.mean(h["status"][idx] == 2), np.mean(ref["status"] == 2)
+    assert abs(ab_o - ab_r) <= 0.03
 
 
 def test_k2_chunking_invariance_at_full_size(trained):

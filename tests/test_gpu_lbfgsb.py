@@ -110,7 +110,9 @@ def _check_against_self_agreement(name, got, ref, w, acts, transform, X0, n):
     print(name, "agree", agree.mean(), "one-sided", one_sided.mean(), "reference self-agreement",
           r_self, "mean dfun ours", d_ours.mean(), "alt", d_alt.mean(),
           "status", np.bincount(got["status"], minlength=3), np.bincount(ref["status"], minlength=3))
-    assert agree.mean() >= min(0.95, r_self - 0.12)
+    # (128 starts: the standard error of a rate near 0.9 is 2.7 points; the 2,048-start runs of
+    # tests/test_gpu_parity_report.py hold the same comparison to 3 points)
+    assert agree.mean() >= min(0.95, r_self - 0.07)
     # no systematic loss of solution quality: mean objective within 3 standard errors of the
     # spread the reference shows against itself
     se = max(np.std(d_alt), np.std(d_ours), 1e-6) / np.sqrt(len(d_ours))
@@ -228,3 +230,90 @@ def test_minimize_with_other_history_sizes_uses_the_generic_core():
         nits[m] = got["nit"]
         _check_against_self_agreement(f"{name} maxcor={m}", got, ref, w, acts, transform, X0, n)
     assert np.mean(nits[3] != nits[10]) >= 0.5
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_non_finite_objective_ends_abnormal(mode):
+    """transform = exp (bore/plugins/hpbandster/base.py:18) overflows fp32 where the logit is
+    below -88: SciPy's line search degenerates on inf / NaN and the start ends ABNORMAL, which the
+    reference's argmax drops (bore/mixins.py:83-85).  The device guard ends such a start with
+    status 2 at once -- in both argmax paths -- and the finite starts are not disturbed."""
+    from bore_b200 import _lib
+    from bore_b200.engine import NativeMLP
+    lib = _lib.require_cuda()
+    dims, acts = [2, 8, 1], ["relu", "linear"]
+    w = [np.array([[1.0, -1.0, 0.5, 0, 0, 0, 0, 0], [0.5, 1.0, -1.0, 0, 0, 0, 0, 0]], np.float32),
+         np.zeros(8, np.float32),
+         np.array([[-400.0], [-300.0], [-200.0], [0], [0], [0], [0], [0]], np.float32), np.zeros(1, np.float32)]
+    net = NativeMLP(dims, acts)
+    net.set_weights(w)
+    X0 = np.random.RandomState(0).uniform(size=(256, 2))
+    f0, _ = km.value_and_input_grad(w, acts, X0, "exp", True, np.float32)
+    bad0 = ~np.isfinite(f0)
+    assert bad0.any() and (~bad0).any()
+    _lib.check(lib.bore_lbfgsb_set_mode(mode))
+    try:
+        net._work = None
+        got = net.lbfgsb(X0, 0.0, 1.0, transform="exp")
+    finally:
+        _lib.check(lib.bore_lbfgsb_set_mode(0))
+    assert set(np.unique(got["status"])) <= {0, 1, 2}
+    assert np.all(got["status"][bad0] == 2) and np.all(got["nit"][bad0] == 0) and np.all(got["nfev"][bad0] == 1)
+    assert np.array_equal(got["x"][bad0], X0[bad0])
+    good = got["status"] != 2
+    assert good.any() and np.all(np.isfinite(got["fun"][good]))
+    assert np.all(got["x"] >= 0.0) and np.all(got["x"] <= 1.0)
+
+
+def test_nan_from_a_callers_objective_through_the_stepper():
+    """bore_lbfgsb_step with f = NaN (or an inf in g) for some starts: those end with status 2 on
+    the step that sees it, at the last good iterate; the others run to convergence."""
+    import torch
+    from bore_b200 import _lib
+    lib = _lib.require_cuda()
+    S, n = 64, 4
+    rs = np.random.RandomState(3)
+    X0 = rs.uniform(-1, 1, size=(S, n))
+    c = rs.uniform(-0.5, 0.5, size=(S, n))
+    lo_a, hi_a = np.full(n, -1.0), np.full(n, 1.0)
+    dev = torch.device("cuda", 0)
+    nbytes = lib.bore_lbfgsb_workspace_bytes(S, n, 10)
+    work = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    xreq = torch.empty(S, n, dtype=torch.float64, device=dev)
+    pend = torch.empty(S, dtype=torch.int32, device=dev)
+    X0d = torch.from_numpy(X0).to(dev)
+    P = lambda t: C.c_void_p(t.data_ptr())
+    NP = lambda a: a.ctypes.data_as(C.c_void_p)
+    _lib.check(lib.bore_lbfgsb_init(P(X0d), S, n, NP(lo_a), NP(hi_a), 10, 1e-9, 1e-5, 1000, 15000,
+                                    20, P(work), nbytes, P(xreq), P(pend), 0, None))
+    fd = torch.zeros(S, dtype=torch.float64, device=dev)
+    gd = torch.zeros(S, n, dtype=torch.float64, device=dev)
+    pending = C.c_int(S)
+    poisoned_f, poisoned_g = np.arange(S) % 8 == 1, np.arange(S) % 8 == 5
+    rounds = 0
+    x_before = {}
+    while pending.value > 0:
+        xr = xreq.cpu().numpy()
+        f = np.sum((xr - c) ** 4 + (xr - c) ** 2, axis=1)
+        g = 4 * (xr - c) ** 3 + 2 * (xr - c)
+        if rounds == 2:  # in mid line search / iteration
+            f[poisoned_f] = np.nan
+            g[poisoned_g, 1] = np.inf
+        fd.copy_(torch.from_numpy(f)); gd.copy_(torch.from_numpy(g))
+        _lib.check(lib.bore_lbfgsb_step(P(fd), P(gd), 1, S, n, P(work), P(xreq), P(pend),
+                                        C.byref(pending), 0, None))
+        rounds += 1
+        assert rounds < 500
+    x = torch.empty(S, n, dtype=torch.float64, device=dev)
+    fun = torch.empty(S, dtype=torch.float64, device=dev)
+    ints = torch.empty(4, S, dtype=torch.int32, device=dev)
+    _lib.check(lib.bore_lbfgsb_results(S, n, P(work), P(x), P(fun), P(ints[0]), P(ints[1]),
+                                       P(ints[2]), P(ints[3]), 0, None))
+    status = ints[2].cpu().numpy()
+    bad = poisoned_f | poisoned_g
+    assert np.all(status[bad] == 2)
+    assert np.all(status[~bad] == 0)
+    assert np.all(np.isfinite(fun.cpu().numpy()))     # the value at the restored iterate
+    xs = x.cpu().numpy()
+    assert np.all(np.isfinite(xs)) and np.all(xs >= -1.0) and np.all(xs <= 1.0)
+    assert np.abs(xs[~bad] - np.clip(c[~bad], -1, 1)).max() <= 1e-3
