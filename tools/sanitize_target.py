@@ -1,0 +1,72 @@
+"""Tiny invocations of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck):
+python tools/sanitize_target.py [k1|k1c|k2|k3|k3f|k3multi|svgd|data|all]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import torch
+from bore_b200 import _lib
+from bore_b200.engine import NativeMLP
+lib = _lib.require_cuda()
+what = sys.argv[1] if len(sys.argv) > 1 else "all"
+rs = np.random.RandomState(0)
+
+
+def glorot(dims, seed):
+    r = np.random.RandomState(seed)
+    ws = []
+    for fi, fo in zip(dims[:-1], dims[1:]):
+        lim = np.sqrt(6.0 / (fi + fo))
+        ws += [r.uniform(-lim, lim, size=(fi, fo)).astype(np.float32), np.zeros(fo, np.float32)]
+    return ws
+
+
+def data(N, D, E):
+    X = rs.uniform(size=(N, D)); y = np.sum((X - 0.4) ** 2, axis=1)
+    z = y < np.quantile(y, 0.25)
+    return X, z, np.stack([rs.permutation(N) for _ in range(E)]).astype(np.int32)
+
+
+dims, acts = [6, 32, 32, 1], ["relu", "relu", "sigmoid"]
+if what in ("k1", "all"):      # one CTA per model
+    net = NativeMLP(dims, acts, n_models=3)
+    for m in range(3): net.set_weights(glorot(dims, m), model=m)
+    net.set_fit_mode(1)
+    X, z, perms = data(150, 6, 2)
+    net.fit_dev(net.to_device(X, np.float32), net.to_device(z.astype(np.float32), np.float32), 150, 64, 2,
+                net.to_device(perms, np.int32), model0=0, count=3)
+    torch.cuda.synchronize(); print("k1 ok")
+if what in ("k1c", "all"):     # one 8-CTA cluster per model
+    d3, a3 = [50, 64, 64, 64, 1], ["relu", "relu", "relu", "sigmoid"]
+    net = NativeMLP(d3, a3); net.set_weights(glorot(d3, 0)); net.set_fit_mode(2)
+    X, z, perms = data(200, 50, 2)
+    print("k1c loss", net.fit(X, z, 2, 64, perms))
+if what in ("k2", "all"):
+    net = NativeMLP(dims, acts); net.set_weights(glorot(dims, 0))
+    f, g = net.value_and_grad(rs.uniform(size=(100, 6)), "identity", True)
+    p = net.predict(rs.uniform(size=(77, 6))); print("k2 ok", f.sum(), p.sum())
+if what in ("k3", "k3f", "all"):
+    for mode, tag in ((1, "k3"), (2, "k3f")):
+        if what not in (tag, "all"): continue
+        _lib.check(lib.bore_lbfgsb_set_mode(mode))
+        net = NativeMLP(dims, acts); net.set_weights(glorot(dims, 1))
+        r = net.lbfgsb(rs.uniform(size=(40, 6)), 0.0, 1.0)
+        print(tag, "ok rounds", r["rounds"], "nit", r["nit"].mean())
+    _lib.check(lib.bore_lbfgsb_set_mode(0))
+if what in ("k3multi", "all"):
+    net = NativeMLP(dims, acts, n_models=4)
+    for m in range(4): net.set_weights(glorot(dims, 10 + m), model=m)
+    for mode in (2, 1):
+        _lib.check(lib.bore_lbfgsb_set_mode(mode)); net._work = None
+        r = net.lbfgsb_multi_dev(torch.from_numpy(rs.uniform(size=(4, 5, 6))).cuda(), 0.0, 1.0)
+        torch.cuda.synchronize()
+    _lib.check(lib.bore_lbfgsb_set_mode(0)); print("k3multi ok")
+if what in ("svgd", "all"):
+    net = NativeMLP(dims, acts); net.set_weights(glorot(dims, 2))
+    x = net.svgd_maximize(rs.uniform(size=(8, 6)), "identity", np.zeros(6), np.ones(6), 5, float("nan"), 1e-3, .9, 1e-6, 1.0, 0.0, 1.0)
+    print("svgd ok", x.shape)
+if what in ("data", "all"):
+    net = NativeMLP(dims, acts)
+    z = net.quantile_labels_dev(torch.from_numpy(rs.normal(size=(3, 101))).cuda(), 1 / 3)
+    k = net.keep_unique_dev(torch.from_numpy(rs.uniform(size=(2, 5, 6))).cuda(), torch.from_numpy(rs.uniform(size=(2, 9, 6))).cuda())
+    torch.cuda.synchronize(); print("data ok")
