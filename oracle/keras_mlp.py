@@ -3,7 +3,47 @@
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  **Parity unpinned** for this file:
 TensorFlow 2.5.0 (reference pin, /root/reference/setup.py:42) is absent from the image,
 so every rule below is written from knowledge of that release and flagged
-[TF-semantics].  Reference call sites each function follows:
+[TF-semantics].  What narrows the risk to the RULES themselves (tests/test_oracle.py):
+value and gradients agree with torch-CPU autograd, and the whole ``fit`` loop agrees with an
+independent torch implementation (autograd gradients, torch's own BCE-with-logits, the Adam
+update written in the textbook beta*m + (1-beta)*g form) to 1e-10 over hundreds of fp64 steps.
+
+The TF 2.5 sources each [TF-semantics] rule restates (paths inside the tensorflow repository at
+tag v2.5.0; cited from knowledge of that tree -- it cannot be opened here):
+
+* Dense                 tensorflow/python/keras/layers/core.py ``Dense.call`` ->
+                        keras/layers/ops/core.py ``dense``: MatMul(inputs, kernel), bias_add,
+                        activation; kernel shape (in, out)
+* glorot_uniform        keras/initializers/initializers_v2.py ``GlorotUniform`` =
+                        VarianceScaling(scale=1, mode="fan_avg", distribution="uniform"):
+                        limit = sqrt(3 * scale / ((fan_in + fan_out) / 2))
+* relu / elu grads      tensorflow/core/kernels/relu_op_functor.h ``ReluGrad`` (gradients *
+                        (features > 0)) and ``EluGrad`` ((activations < 0).select((activations + 1)
+                        * gradients, gradients)) -- both through the layer OUTPUT;
+                        sigmoid / tanh: core/kernels/cwise_ops_gradients.h (y (1 - y) dy, (1 - y^2) dy)
+* "binary_crossentropy" keras/backend.py ``binary_crossentropy``: for a graph tensor produced by a
+  on a sigmoid output   ``Sigmoid`` op the logits are taken from ``output.op.inputs[0]`` and
+                        from_logits is set ("we use logits from the sigmoid function directly");
+                        otherwise clip to [eps, 1 - eps] and the log form.  Then
+                        python/ops/nn_impl.py ``sigmoid_cross_entropy_with_logits``:
+                        relu(x) - x z + log1p(exp(-|x|))
+* loss reduction        keras/losses.py ``LossFunctionWrapper`` with
+                        ReductionV2.SUM_OVER_BATCH_SIZE; regularisers added by
+                        keras/engine/compile_utils.py ``LossesContainer.__call__``
+* Adam                  keras/optimizer_v2/adam.py ``Adam._resource_apply_dense`` ->
+                        ResourceApplyAdam, core/kernels/training_ops.cc ``ApplyAdam``:
+                        alpha = lr sqrt(1 - beta2^t) / (1 - beta1^t); m += (g - m)(1 - beta1);
+                        v += (g^2 - v)(1 - beta2); var -= (m alpha) / (sqrt(v) + epsilon);
+                        epsilon = backend_config.epsilon() = 1e-7; t = iterations + 1
+* fit / batches         keras/engine/training.py ``Model.fit`` with
+                        keras/engine/data_adapter.py ``TensorLikeDataAdapter``: per epoch
+                        ``random_ops.random_shuffle(range(N))``, ``slice_batch_indices``: full
+                        batches + one partial batch; epoch loss = keras/metrics.py ``Mean`` with
+                        sample_weight = batch size (compile_utils.py ``LossesContainer``)
+* accuracy on logits    keras/metrics.py ``binary_accuracy(y_true, y_pred, threshold=0.5)`` applied
+                        to the raw output (plugin quirk, logging only)
+
+Reference call sites each function follows:
 
 * ``dense_sequential_dims``     -> bore/models.py:9-21  (layer-count quirk)
 * ``forward`` / ``predict``     -> Keras ``Sequential.__call__`` / ``predict`` as used at

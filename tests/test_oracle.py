@@ -144,3 +144,68 @@ def test_oracle_reproduces_fit_golden():
         hist, _ = km.fit(w, acts, g[name + "/X"], g[name + "/z"], len(perms), 64, perms,
                          l2=float(g[name + "/l2"]))
         assert np.abs(hist - g[name + "/loss"]).max() <= 1e-5
+
+
+# ---------------------------------------------------------------------------- the whole fit loop
+def _torch_fit(w0, acts, X, z, epochs, batch, perms, l2=0.0, lr=1e-3, b1=0.9, b2=0.999, eps=1e-7):
+    """An independent implementation of what ``oracle.keras_mlp.fit`` restates: gradients by
+    autograd (not the hand-written backward pass), torch's own binary_cross_entropy_with_logits,
+    Adam in the textbook form  m = b1 m + (1 - b1) g,  v = b2 v + (1 - b2) g^2,
+    w -= lr_t m / (sqrt(v) + eps)  with  lr_t = lr sqrt(1 - b2^t) / (1 - b1^t)  (Keras: eps is
+    OUTSIDE the bias correction), epoch loss = sum(batch loss * batch size) / N.  fp64."""
+    F = torch.nn.functional
+    act_fn = {"linear": lambda t: t, "relu": torch.relu, "elu": F.elu, "sigmoid": torch.sigmoid,
+              "tanh": torch.tanh}
+    ws = [torch.tensor(np.asarray(a, np.float64), requires_grad=True) for a in w0]
+    m = [torch.zeros_like(a) for a in ws]
+    v = [torch.zeros_like(a) for a in ws]
+    Xt, zt = torch.tensor(np.asarray(X, np.float64)), torch.tensor(np.asarray(z, np.float64)).reshape(-1, 1)
+    N, t, hist = Xt.shape[0], 0, []
+    for e in range(epochs):
+        tot = 0.0
+        perm = torch.as_tensor(np.asarray(perms[e], np.int64))
+        for s in range(0, N, batch):
+            idx = perm[s:s + batch]
+            h = Xt[idx]
+            for l, a in enumerate(acts):
+                h = h @ ws[2 * l] + ws[2 * l + 1]
+                if l < len(acts) - 1:
+                    h = act_fn[a](h)
+            loss = F.binary_cross_entropy_with_logits(h, zt[idx], reduction="mean")  # on the logits
+            if l2:
+                loss = loss + sum(l2 * (a * a).sum() for a in ws)
+            grads = torch.autograd.grad(loss, ws)
+            tot += float(loss) * len(idx)
+            t += 1
+            lr_t = lr * np.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
+            with torch.no_grad():
+                for i, g in enumerate(grads):
+                    m[i] = b1 * m[i] + (1.0 - b1) * g
+                    v[i] = b2 * v[i] + (1.0 - b2) * g * g
+                    ws[i] -= lr_t * m[i] / (torch.sqrt(v[i]) + eps)
+        hist.append(tot / N)
+    return np.array(hist), [a.detach().numpy() for a in ws], t
+
+
+@pytest.mark.parametrize("name,l2", [("cfg2_hartmann6", 0.0), ("cfg5_plugin8", 0.0), ("cfg5_plugin8", 1e-4),
+                                     ("tanh_exp", 0.0), ("cfg1_branin", 0.0)])
+def test_fit_loop_vs_independent_torch_implementation(name, l2):
+    """>= 300 Adam steps in fp64: loss trajectory and final weights to 1e-10.  Narrows the
+    unpinned half of the oracle to the [TF-semantics] RULES (which formula Keras uses), away from
+    their implementation here."""
+    dims, acts, _ = NETS[name]
+    acts = list(acts[:-1]) + ["sigmoid" if acts[-1] == "sigmoid" else "linear"]
+    rs = np.random.RandomState(12)
+    N, E, B = 150, 100, 64                      # 3 steps per epoch (the last batch is short): 300 steps
+    X = rs.uniform(size=(N, dims[0]))
+    y = np.sum((X - 0.45) ** 2, axis=1)
+    z = y < np.quantile(y, 0.3)
+    perms = np.stack([rs.permutation(N) for _ in range(E)])
+    w0 = km.init_weights(dims, 3, np.float64)
+    w = [a.copy() for a in w0]
+    hist, adam = km.fit(w, acts, X, z, E, B, perms, l2=l2, dtype=np.float64)
+    hist_t, w_t, t = _torch_fit(w0, acts, X, z, E, B, perms, l2=l2)
+    assert adam.t == t == 300
+    assert np.abs(hist - hist_t).max() <= 1e-10, np.abs(hist - hist_t).max()
+    assert max(np.abs(a - b).max() for a, b in zip(w, w_t)) <= 1e-10
+    assert hist[-1] < hist[0]
