@@ -64,9 +64,11 @@ SIGNATURES = {
                                              vp, C.c_size_t, vp, vp, vp, vp, vp, vp,
                                              c_int_p, C.POINTER(C.c_longlong), vp]),
     "bore_select_best_groups": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, C.c_int, vp]),
+    "bore_allreduce_maxloc": (C.c_int, [vp, vp, vp]),
     "bore_quantile_labels": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, vp, vp, vp, C.c_int, vp]),
     "bore_is_duplicate": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_double, C.c_double,
                                     vp, vp, C.c_int, vp]),
+    "bore_truncnorm_distort": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, vp, vp, vp, vp, C.c_int, vp]),
     "bore_svgd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "bore_svgd_maximize": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_double, C.c_int,
                                      C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,

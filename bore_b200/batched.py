@@ -199,14 +199,18 @@ class BatchedMaximizableSequential:
     # ------------------------------------------------------------------ argmax per problem
     def argmax(self, bounds, num_starts=5, num_samples=1024, method="L-BFGS-B",
                options=dict(maxiter=1000, ftol=1e-9), random_state=None, X_init=None,
-               exclude=None, rtol=1e-5, atol=1e-8):
+               exclude=None, rtol=1e-5, atol=1e-8, distortion=None):
         """One ``OptimizeResult`` (or None) per problem (``BatchedResults``, a lazy sequence):
         bore/mixins.py:22-89 for each of them.
         ``random_state`` draws the (M, num_samples, D) screening samples problem after problem
         (what M sequential ``argmax`` calls sharing one RandomState would consume); ``X_init``
         overrides the draw.  ``exclude`` (M, N, D): each problem's stored observations -- results
         ``np.allclose`` to one of them are dropped before the selection, which is the plugin's
-        ``filter_fn=_is_unique`` (bore/plugins/hpbandster/base.py:227-231, bore/data.py:42-48)."""
+        ``filter_fn=_is_unique`` (bore/plugins/hpbandster/base.py:227-231, bore/data.py:42-48).
+        ``distortion``: the plugin's truncated-normal resample of the suggestion
+        (``maybe_distort``, bore/base.py:45-64; plugins/hpbandster/base.py:266) applied to every
+        problem's winner on the device; the uniform variates come from ``random_state`` AFTER the
+        screening samples, one row per problem (problems without a winner consume theirs too)."""
         import torch
         assert num_samples >= num_starts > 0
         if method != "L-BFGS-B":
@@ -218,6 +222,8 @@ class BatchedMaximizableSequential:
         if X_init is None:
             rs = check_random_state(random_state)
             X_init = rs.uniform(low=low, high=high, size=(M, num_samples, dim))
+        else:
+            rs = check_random_state(random_state) if distortion is not None else None
         X_init = np.asarray(X_init, np.float64)
         assert X_init.shape == (M, num_samples, dim)
         X64 = net.to_device(X_init, np.float64)
@@ -244,6 +250,9 @@ class BatchedMaximizableSequential:
         win = (0x7fffffff - (keys & 0x7fffffff)).clamp(0, num_starts - 1)
         pick = lambda t: torch.gather(t, 1, win.unsqueeze(-1)).squeeze(-1)
         xw = torch.gather(res["x"], 1, win.view(M, 1, 1).expand(-1, 1, dim)).squeeze(1)
+        if distortion is not None:
+            u = net.to_device(rs.uniform(size=(M, dim)), np.float64)
+            xw = net.distort_dev(xw.contiguous(), distortion, low, high, u)
         rec = torch.cat([xw, pick(res["fun"]).unsqueeze(-1)] +
                         [pick(res[k]).to(torch.float64).unsqueeze(-1) for k in ("nit", "nfev", "status", "task")] +
                         [keys.to(torch.float64).unsqueeze(-1)], dim=1).cpu().numpy()

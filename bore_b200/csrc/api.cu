@@ -190,6 +190,7 @@ int bore_mlp_params_dev(bore_mlp *h, float **params_dev) {
 
 int bore_mlp_predict(bore_mlp *h, int model, const float *X_dev, int S, float *out_dev,
                      void *stream) {
+  BORE_NVTX("bore:predict (K0)");
   CHECK_MODEL(h, model);
   BORE_CHECK(S >= 0, "bore_mlp_predict: S=%d", S);
   return launch_mlp_eval(h, model, false, BORE_TRANSFORM_IDENTITY, 0, X_dev, S, out_dev, nullptr,
@@ -210,6 +211,7 @@ int bore_mlp_predict_multi(bore_mlp *h, int model0, int n_models, const float *X
 
 int bore_mlp_value_and_grad(bore_mlp *h, int model, int transform, int negate, const float *X_dev,
                             int S, float *f_dev, float *g_dev, void *stream) {
+  BORE_NVTX("bore:value_and_grad (K2)");
   CHECK_MODEL(h, model);
   BORE_CHECK(S >= 0, "bore_mlp_value_and_grad: S=%d", S);
   BORE_CHECK(transform >= 0 && transform <= BORE_TRANSFORM_EXP, "unknown transform code %d",

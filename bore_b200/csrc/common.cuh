@@ -29,6 +29,15 @@ void bore_set_error(const char *fmt, ...);
     }                                                                            \
   } while (0)
 
+// ---------------------------------------------------------------- NVTX ranges
+// Header-only NVTX 3: a no-op unless a tool (nsys, ncu --nvtx) injects itself; no link dependency.
+#include <nvtx3/nvToolsExt.h>
+struct BoreNvtxRange {
+  explicit BoreNvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~BoreNvtxRange() { nvtxRangePop(); }
+};
+#define BORE_NVTX(name) BoreNvtxRange bore_nvtx_range__(name)
+
 // ---------------------------------------------------------------- model descriptor
 // Passed by value to kernels (lives in kernel parameter space / constant bank).
 struct MlpDesc {

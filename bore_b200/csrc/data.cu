@@ -129,6 +129,37 @@ duplicate_kernel(const double *__restrict__ x, int n_groups, int per_group,
 
 int pow2_at_least(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
+// maybe_distort (bore/base.py:45-64): x = truncnorm(a, b, loc, scale).rvs(random_state) with
+// a = (lower - loc) / scale, b = (upper - loc) / scale.  scipy draws ONE uniform variate per
+// coordinate from the caller's MT19937 stream and maps it through the distribution's ppf; the
+// variates are drawn on the host (stream parity) and uploaded, the ppf runs here:
+//   a <  0:  x =  ndtri(Phi(a)  + q       * mass)
+//   a >= 0:  x = -ndtri(Phi(-b) + (1 - q) * mass)        (right tail through the survival side)
+// with mass = Phi(b) - Phi(a) taken on the side where it does not cancel -- scipy's case split
+// (scipy/stats/_continuous_distns.py, truncnorm_gen._ppf / _log_gauss_mass) without the detour
+// through logarithms, which only matters for intervals deep in one tail (loc lies inside the box
+// here).  One thread per coordinate.
+__global__ void __launch_bounds__(256)
+truncnorm_distort_kernel(const double *__restrict__ loc, long n_total, int D, double scale,
+                         const double *__restrict__ lo, const double *__restrict__ hi,
+                         const double *__restrict__ u, double *__restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_total) return;
+  const int d = (int)(i % D);
+  const double l = loc[i], q = u[i];
+  const double a = (lo[d] - l) / scale, b = (hi[d] - l) / scale;
+  double mass;
+  if (b <= 0.0) mass = normcdf(b) - normcdf(a);
+  else if (a > 0.0) mass = normcdf(-a) - normcdf(-b);
+  else mass = 1.0 - normcdf(a) - normcdf(-b);
+  double x;
+  if (a < 0.0) x = normcdfinv(normcdf(a) + q * mass);
+  else x = -normcdfinv(normcdf(-b) + (1.0 - q) * mass);
+  // the standardised variate lies in [a, b] up to rounding: clamp like the support does
+  x = fmin(fmax(x, a), b);
+  out[i] = l + scale * x;
+}
+
 }  // namespace
 
 extern "C" {
@@ -169,6 +200,21 @@ int bore_is_duplicate(const double *x_dev, int n_groups, int per_group, const do
   const int blocks = (int)((warps * 32 + 255) / 256);
   duplicate_kernel<<<blocks, 256, 0, (cudaStream_t)stream_>>>(x_dev, n_groups, per_group, x_prev_dev,
                                                              n_prev, D, rtol, atol, dup_dev, keep_dev);
+  BORE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bore_truncnorm_distort(const double *loc_dev, int n_points, int D, double scale,
+                           const double *lo_dev, const double *hi_dev, const double *u_dev,
+                           double *out_dev, int device, void *stream_) {
+  BORE_CHECK(bore_device_count() > 0, "no CUDA device visible -- bore_b200 has no CPU fallback");
+  BORE_CHECK(n_points >= 1 && D >= 1, "bore_truncnorm_distort: n_points=%d, D=%d", n_points, D);
+  BORE_CHECK(scale > 0.0, "bore_truncnorm_distort: scale must be positive");
+  BORE_CHECK(loc_dev && lo_dev && hi_dev && u_dev && out_dev, "bore_truncnorm_distort: NULL buffer");
+  BORE_CUDA(cudaSetDevice(device));
+  const long n_total = (long)n_points * D;
+  truncnorm_distort_kernel<<<(int)((n_total + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
+      loc_dev, n_total, D, scale, lo_dev, hi_dev, u_dev, out_dev);
   BORE_CUDA(cudaGetLastError());
   return 0;
 }

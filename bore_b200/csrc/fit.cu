@@ -1161,6 +1161,7 @@ extern "C" {
 int bore_mlp_fit(bore_mlp *h, int model0, int count, const float *X_dev, const float *z_dev, int N,
                  int shared_data, int batch_size, int epochs, const int32_t *perm_dev,
                  int shared_perm, float *loss_out_dev, void *stream) {
+  BORE_NVTX("bore:fit (K1)");
   BORE_CHECK(h != nullptr, "NULL handle");
   BORE_CHECK(model0 >= 0 && count >= 1 && model0 + count <= h->n_models,
              "bore_mlp_fit: models [%d,%d) outside [0,%d)", model0, model0 + count, h->n_models);

@@ -704,6 +704,7 @@ static int minimize_impl(bore_mlp *h, int model, int n_models, int per_model, in
                          void *work_dev, size_t work_bytes, double *x_dev, double *fun_dev,
                          int32_t *nit_dev, int32_t *nfev_dev, int32_t *status_dev, int32_t *task_dev,
                          int *rounds_out, long long *evals_out, void *stream_) {
+  BORE_NVTX("bore:argmax L-BFGS-B (K2+K3 / K3f)");
   BORE_CHECK(h != nullptr, "NULL handle");
   BORE_CHECK(model >= 0 && n_models >= 1 && model + n_models <= h->n_models,
              "models [%d,%d) outside [0,%d)", model, model + n_models, h->n_models);

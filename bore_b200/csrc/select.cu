@@ -246,4 +246,31 @@ int bore_select_best_groups(const double *fun_dev, const int32_t *status_dev,
   return 0;
 }
 
+// C1: the single collective of the multi-GPU argmax.  NCCL has ncclMax but no
+// MAXLOC, so value and location travel in one int64 key (bore_select_best); this is
+// ncclAllReduce(key, key, 1, ncclInt64, ncclMax, comm, stream) for hosts that do not go through
+// torch.distributed.  NCCL is resolved at call time from the process (whatever libnccl.so.2 the
+// host already loaded, else the system one), so libbore_b200.so has no link-time dependency on it.
+#include <dlfcn.h>
+int bore_allreduce_maxloc(void *nccl_comm, int64_t *key_dev, void *stream) {
+  BORE_CHECK(nccl_comm != nullptr && key_dev != nullptr, "bore_allreduce_maxloc: NULL argument");
+  typedef int (*allreduce_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+  typedef const char *(*errstr_fn)(int);
+  static allreduce_fn fn = nullptr;
+  static errstr_fn es = nullptr;
+  if (!fn) {
+    void *hnd = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!hnd) hnd = dlopen("libnccl.so.2", RTLD_NOW);
+    if (!hnd) hnd = dlopen("libnccl.so", RTLD_NOW);
+    BORE_CHECK(hnd != nullptr, "bore_allreduce_maxloc: cannot load libnccl.so.2 (%s)", dlerror());
+    fn = reinterpret_cast<allreduce_fn>(dlsym(hnd, "ncclAllReduce"));
+    es = reinterpret_cast<errstr_fn>(dlsym(hnd, "ncclGetErrorString"));
+    BORE_CHECK(fn != nullptr, "bore_allreduce_maxloc: ncclAllReduce not found");
+  }
+  // nccl.h: ncclInt64 = 4, ncclMax = 2 (stable since NCCL 2.0)
+  const int rc = fn(key_dev, key_dev, 1, 4, 2, nccl_comm, (cudaStream_t)stream);
+  BORE_CHECK(rc == 0, "bore_allreduce_maxloc: ncclAllReduce -> %s", es ? es(rc) : "error");
+  return 0;
+}
+
 }  // extern "C"

@@ -312,6 +312,7 @@ int bore_svgd_maximize(bore_mlp *h, int model0, int n_problems, int transform, d
                        const double *lo_host, const double *hi_host, double length_scale, int n_iter,
                        double step_size, double alpha, double eps, double tau, double lambd, double zeta_c,
                        void *work_dev, size_t work_bytes, void *stream_) {
+  BORE_NVTX("bore:argmax_batch SVGD (K6)");
   BORE_CHECK(h != nullptr, "bore_svgd_maximize: NULL handle");
   BORE_CHECK(bore_device_count() > 0, "no CUDA device visible -- bore_b200 has no CPU fallback");
   BORE_CHECK(n_problems >= 1 && model0 >= 0 && model0 + n_problems <= h->n_models,

@@ -390,6 +390,20 @@ class NativeMLP:
                                               None, _ptr(keep), self.device, self._stream()))
         return keep
 
+    def distort_dev(self, loc_dev, distortion, low, high, u_dev):
+        """loc_dev (P, D) float64 suggestions -> truncated-normal resamples around them
+        (bore/base.py:45-64) from the uniform variates u_dev (P, D) drawn on the host."""
+        torch = _torch()
+        P, D = loc_dev.shape
+        assert loc_dev.dtype == torch.float64 and loc_dev.is_contiguous()
+        assert u_dev.shape == (P, D) and u_dev.dtype == torch.float64 and u_dev.is_contiguous()
+        lo = self.to_device(np.broadcast_to(np.asarray(low, np.float64), (D,)), np.float64)
+        hi = self.to_device(np.broadcast_to(np.asarray(high, np.float64), (D,)), np.float64)
+        out = torch.empty_like(loc_dev)
+        _lib.check(self.lib.bore_truncnorm_distort(_ptr(loc_dev), int(P), int(D), float(distortion), _ptr(lo),
+                                                   _ptr(hi), _ptr(u_dev), _ptr(out), self.device, self._stream()))
+        return out
+
     # ------------------------------------------------------------------ SVGD (section 8f row 3)
     def svgd_maximize(self, x_init, transform, low, high, n_iter, length_scale, step_size, alpha, eps,
                       tau, lambd, zeta_c, model0=0):

@@ -236,6 +236,15 @@ int bore_select_best_groups(const double *fun_dev, const int32_t *status_dev,
                             const uint8_t *keep_dev, int n_groups, int per_group, int64_t *keys_dev,
                             int device, void *stream);
 
+/* ---- C1: the one collective of the sharded argmax ---------------------------------------
+ * Every rank holds the same weights and its own shard of the start points (the loop of
+ * bore/mixins.py:57-61 split over the GPUs); bore_select_best(..., idx_offset = first global
+ * index of the shard) gives its packed key, and ONE max all-reduce agrees on the winner:
+ * ncclAllReduce(ncclMax, ncclInt64, count 1) on `nccl_comm` (an ncclComm_t), in place, on
+ * `stream`.  The winner's global index is 0x7fffffff - (key & 0x7fffffff); key 0 = no start
+ * qualified on any rank.  NCCL is looked up in the process at call time (no link dependency). */
+int bore_allreduce_maxloc(void *nccl_comm, int64_t *key_dev, void *stream);
+
 /* ---- data step either side of the path --------------------
  * bore_quantile_labels replaces Record.load_classification_data (bore/data.py:31-35) for
  * n_problems target vectors y_dev [n_problems][N] (fp64) at once: tau = np.quantile(y, q)
@@ -251,6 +260,15 @@ int bore_select_best_groups(const double *fun_dev, const int32_t *status_dev,
  * |x_prev - x| <= atol + rtol*|x| (x finite) or x_prev == x.  dup_dev / keep_dev (each may be
  * NULL) receive the flag / its negation per candidate; keep_dev is the mask bore_select_best
  * and bore_select_best_groups take.                                                       */
+/* bore_truncnorm_distort replaces maybe_distort / truncated_normal (bore/base.py:45-64) for
+ * n_points suggestions at once: out = truncnorm(a, b, loc, scale).rvs with a = (lo - loc)/scale,
+ * b = (hi - loc)/scale per coordinate.  u_dev [n_points][D] holds the uniform variates scipy's
+ * rvs would draw from the caller's random_state (one per coordinate, in order: draw them on the
+ * host with random_state.uniform(size=(n_points, D)) to keep the stream), lo_dev / hi_dev [D].
+ * Within 1e-9 of scipy (fp64 normcdf / normcdfinv instead of scipy's log-space ppf).       */
+int bore_truncnorm_distort(const double *loc_dev, int n_points, int D, double scale,
+                           const double *lo_dev, const double *hi_dev, const double *u_dev,
+                           double *out_dev, int device, void *stream);
 int bore_quantile_labels(const double *y_dev, int n_problems, int N, double q, float *z_f32_dev,
                          uint8_t *z_u8_dev, double *tau_dev, int device, void *stream);
 int bore_is_duplicate(const double *x_dev, int n_groups, int per_group, const double *x_prev_dev,

@@ -153,3 +153,28 @@ def test_batched_fit_from_raw_targets_and_exclude():
     for p in range(M):
         assert r1[p] is None or not np.allclose(r1[p].x, r0[p].x, rtol=1e-5, atol=1e-8)
         assert r1[p] is None or r1[p].fun >= r0[p].fun
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("D,distortion", [(2, 0.05), (8, 0.01), (50, 0.2)])
+def test_truncnorm_distort_matches_scipy_with_the_same_random_state(D, distortion):
+    """maybe_distort on the device (bore/base.py:45-64): the reference draws through scipy's
+    truncnorm.rvs from the caller's random_state; the batch version consumes the same variates
+    in the same order and reproduces the values (1e-9)."""
+    from scipy.optimize import Bounds
+    from bore_b200.base import maybe_distort, maybe_distort_batch
+    from bore_b200.engine import NativeMLP
+    net = NativeMLP([D, 4, 1], ["relu", "sigmoid"])
+    rs = np.random.RandomState(3)
+    P = 37
+    loc = rs.uniform(size=(P, D))
+    loc[0] = 0.0; loc[1] = 1.0; loc[2, ::2] = 0.0; loc[3] = 1e-12     # suggestions on the faces of the box
+    bounds = Bounds(np.zeros(D), np.ones(D))
+    rs_ref, rs_dev = np.random.RandomState(11), np.random.RandomState(11)
+    ref = np.stack([maybe_distort(loc[p], distortion, bounds, rs_ref, print_fn=lambda s: None) for p in range(P)])
+    got = maybe_distort_batch(loc, distortion, bounds, rs_dev, net=net)
+    assert got.shape == (P, D)
+    assert np.all(got >= 0.0) and np.all(got <= 1.0)
+    assert np.abs(got - ref).max() <= 1e-9, np.abs(got - ref).max()
+    assert rs_ref.uniform() == rs_dev.uniform()                      # both consumed the same stream
+    assert np.array_equal(maybe_distort_batch(loc, None), loc)       # distortion=None: untouched

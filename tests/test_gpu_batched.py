@@ -88,3 +88,28 @@ def test_batched_all_samples_are_starts_and_many_problems():
         assert abs(float(f_chk[0]) - float(r.fun)) <= 1e-5
         ok += 1
     assert ok > 0
+
+
+def test_batched_argmax_distortion_is_maybe_distort_per_problem():
+    """``distortion=`` resamples every problem's winner exactly like the plugin's host call
+    (bore/plugins/hpbandster/base.py:266 -> bore/base.py:51-64) with the same random_state."""
+    from scipy.optimize import Bounds
+    from bore_b200 import BatchedMaximizableSequential, Dense, maybe_distort
+    M, D = 5, 6
+    dims = [D, 32, 32, 1]
+    layers = [Dense(32, activation="relu", input_dim=D), Dense(32, activation="relu"), Dense(1, activation="sigmoid")]
+    model = BatchedMaximizableSequential(layers, n_problems=M, seed=2)
+    model.compile(optimizer="adam", loss="binary_crossentropy")
+    model.set_weights([km.init_weights(dims, 40 + p) for p in range(M)])
+    X_init = np.random.RandomState(1).uniform(size=(M, 64, D))
+    bounds = [(0.0, 1.0)] * D
+    plain = model.argmax(bounds, num_starts=4, num_samples=64, X_init=X_init)
+    dist = model.argmax(bounds, num_starts=4, num_samples=64, X_init=X_init, distortion=0.05,
+                        random_state=np.random.RandomState(9))
+    rs = np.random.RandomState(9)
+    b = Bounds(np.zeros(D), np.ones(D))
+    for p in range(M):
+        want = maybe_distort(plain[p].x, 0.05, b, rs, print_fn=lambda s: None)
+        assert np.abs(dist[p].x - want).max() <= 1e-9
+        assert np.all(dist[p].x >= 0) and np.all(dist[p].x <= 1)
+        assert dist[p].fun == plain[p].fun      # the record still describes the optimum found

@@ -160,3 +160,29 @@ def test_convert_drives_scipy_and_multi_start():
         assert q.success and np.abs(q.x - 0.3).max() <= 1e-5
     with pytest.raises(NotImplementedError):
         model.argmax(bounds, method="BFGS", print_fn=None)
+
+
+def test_allreduce_maxloc_through_the_c_abi_with_a_raw_nccl_communicator():
+    """bore_allreduce_maxloc: the collective is reachable without torch -- a
+    communicator made with NCCL's own ncclCommInitAll (one rank here; tools/nccl_maxloc_2gpu.py
+    runs two), the packed key reduced in place."""
+    import ctypes as C
+    import torch
+    from bore_b200 import _lib
+    lib = _lib.require_cuda()
+    try:
+        nccl = C.CDLL("libnccl.so.2")
+    except OSError:
+        pytest.skip("no libnccl.so.2 on the loader path")
+    comm = C.c_void_p()
+    devs = (C.c_int * 1)(0)
+    assert nccl.ncclCommInitAll(C.byref(comm), 1, devs) == 0
+    try:
+        key = torch.tensor([0x3F80000012345678], dtype=torch.int64, device="cuda:0")
+        stream = torch.cuda.current_stream(0).cuda_stream
+        _lib.check(lib.bore_allreduce_maxloc(comm, C.c_void_p(key.data_ptr()), C.c_void_p(stream)))
+        torch.cuda.synchronize()
+        assert int(key.item()) == 0x3F80000012345678
+    finally:
+        nccl.ncclCommDestroy(comm)
+    assert lib.bore_allreduce_maxloc(None, None, None) != 0      # loud on bad arguments
