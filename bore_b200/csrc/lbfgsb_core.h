@@ -59,8 +59,13 @@
 #define LB_SHARED(p) ((void)0)
 #else
 #define LB_UNROLL1 _Pragma("unroll 1")
+#ifdef LB_COMPACT  // the includer trades dynamic instructions for instruction footprint
+#define LB_UNROLL_HOT _Pragma("unroll 1")
+#define LB_UNROLL_HOT2 _Pragma("unroll 1")
+#else
 #define LB_UNROLL_HOT _Pragma("unroll 2")   // hot inner loops: loads of 2 iterations in flight
 #define LB_UNROLL_HOT2 _Pragma("unroll 2")
+#endif
 #define LB_NI __device__ __noinline__
 #define LB_SHARED(p) __builtin_assume(__isShared(p))
 #endif

@@ -44,6 +44,11 @@
 #include "lbfgsb_fused.h"
 #include "lbfgsb_types.h"
 
+// The fused kernel is bound by instruction fetch (free-running warps, ~90 KB executed footprint):
+// its copy of the core keeps the hot inner loops rolled (BORE: -DLB_FUSED_UNROLL restores unroll 2).
+#ifndef LB_FUSED_UNROLL
+#define LB_COMPACT 1
+#endif
 namespace lbf {  // warp-collective variant of the core, run-time history size m
 #define LB_VARIANT 1
 #include "lbfgsb_core.h"

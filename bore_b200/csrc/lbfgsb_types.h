@@ -82,13 +82,31 @@ struct LbScal {
 // ------------------------------------------------------------------ More'-Thuente step (dcstep)
 LB_HD void lb_dcstep(double &stx, double &fx, double &dx, double &sty, double &fy, double &dy,
                      double &stp, double fp, double dp, int &brackt, double stpmin, double stpmax) {
+  // The four cases of the original share one cubic-interpolation kernel
+  //   theta = 3 (fa - fp) / (stp - sta) + da + dp,  s = max(|theta|, |da|, |dp|),
+  //   gamma = +-s sqrt((theta/s)^2 - (da/s)(dp/s))
+  // taken on the pair (sta, fa, da) = the x end point (cases 1-3) or the y end point (case 4).  It
+  // is written ONCE here (same operations in the same order as the four copies of the original, so
+  // the results are bit-identical): on the device the three divisions and the square root are
+  // ~120 instructions, and four copies of them were 15 KB of instruction footprint for a routine
+  // that runs once per step (profiles/r02_notes.md).
   const double sgnd = dp * (dx / fabs(dx));
+  const int kase = fp > fx ? 1 : (sgnd < 0.0 ? 2 : (fabs(dp) < fabs(dx) ? 3 : 4));
   double stpf;
-  if (fp > fx) {
-    const double theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
-    const double s = fmax(fabs(theta), fmax(fabs(dx), fabs(dp)));
-    double gamma = s * sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
-    if (stp < stx) gamma = -gamma;
+  double theta = 0.0, gamma = 0.0;
+  if (kase != 4 || brackt) {
+    const bool yend = kase == 4;
+    const double sta = yend ? sty : stx, fa = yend ? fy : fx, da = yend ? dy : dx;
+    // (cases 1-3: 3 (fx - fp) / (stp - stx); case 4: 3 (fp - fy) / (sty - stp) -- the same quotient)
+    theta = (yend ? 3.0 * (fp - fa) / (sta - stp) : 3.0 * (fa - fp) / (stp - sta)) + da + dp;
+    const double s = fmax(fabs(theta), fmax(fabs(da), fabs(dp)));
+    double rad = (theta / s) * (theta / s) - (da / s) * (dp / s);
+    if (kase == 3) rad = fmax(0.0, rad);
+    gamma = s * sqrt(rad);
+    const bool flip = kase == 1 ? stp < stx : (kase == 4 ? stp > sty : stp > stx);
+    if (flip) gamma = -gamma;
+  }
+  if (kase == 1) {
     const double p = (gamma - dx) + theta;
     const double q = ((gamma - dx) + gamma) + dp;
     const double r = p / q;
@@ -97,11 +115,7 @@ LB_HD void lb_dcstep(double &stx, double &fx, double &dx, double &sty, double &f
     if (fabs(stpc - stx) < fabs(stpq - stx)) stpf = stpc;
     else stpf = stpc + (stpq - stpc) / 2.0;
     brackt = 1;
-  } else if (sgnd < 0.0) {
-    const double theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
-    const double s = fmax(fabs(theta), fmax(fabs(dx), fabs(dp)));
-    double gamma = s * sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
-    if (stp > stx) gamma = -gamma;
+  } else if (kase == 2) {
     const double p = (gamma - dp) + theta;
     const double q = ((gamma - dp) + gamma) + dx;
     const double r = p / q;
@@ -110,11 +124,7 @@ LB_HD void lb_dcstep(double &stx, double &fx, double &dx, double &sty, double &f
     if (fabs(stpc - stp) > fabs(stpq - stp)) stpf = stpc;
     else stpf = stpq;
     brackt = 1;
-  } else if (fabs(dp) < fabs(dx)) {
-    const double theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
-    const double s = fmax(fabs(theta), fmax(fabs(dx), fabs(dp)));
-    double gamma = s * sqrt(fmax(0.0, (theta / s) * (theta / s) - (dx / s) * (dp / s)));
-    if (stp > stx) gamma = -gamma;
+  } else if (kase == 3) {
     const double p = (gamma - dp) + theta;
     const double q = (gamma + (dx - dp)) + gamma;
     const double r = p / q;
@@ -136,10 +146,6 @@ LB_HD void lb_dcstep(double &stx, double &fx, double &dx, double &sty, double &f
     }
   } else {
     if (brackt) {
-      const double theta = 3.0 * (fp - fy) / (sty - stp) + dy + dp;
-      const double s = fmax(fabs(theta), fmax(fabs(dy), fabs(dp)));
-      double gamma = s * sqrt((theta / s) * (theta / s) - (dy / s) * (dp / s));
-      if (stp > sty) gamma = -gamma;
       const double p = (gamma - dp) + theta;
       const double q = ((gamma - dp) + gamma) + dy;
       const double r = p / q;

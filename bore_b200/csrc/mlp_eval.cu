@@ -5,9 +5,13 @@
 // convert() (bore/base.py:35-42, bore/decorators.py:48-65) with transform(-u)
 // (bore/mixins.py:20).
 //
-// Mapping.  Weights (forward layout W[k][j] and, for the reverse pass, the transposed
-// layout WT[j][k]) are staged once per CTA into shared memory, zero-padded so that every
-// inner loop is branch-free.  Each WARP owns tiles of 16 points and carries them through
+// Mapping.  Weights are staged once per CTA into shared memory in ONE layout, W[k][j] with leading
+// dimension (units rounded up to a chunk) + 4, zero-padded so that every inner loop is branch-free.
+// The forward pass reads rows (a lane's 4 adjacent units: one LDS.128, lanes contiguous); the
+// reverse pass reads the SAME image along j -- a lane owns input units ug, ug+UG, ug+2UG, ug+3UG of
+// a chunk, so that the 8 lanes of a quarter-warp read 8 consecutive rows: stride LD = 4 (mod 32)
+// words, 32 distinct banks per LDS.128.  (Round 1 kept a transposed copy for the reverse pass:
+// 98 KB instead of 53 KB at Dense64x3, i.e. 11 instead of 14 resident warps per SM.)  Each WARP owns tiles of 16 points and carries them through
 // all layers on its own: activations live in a per-warp shared-memory strip laid out
 // [unit][point] (row stride 20 floats), so layers hand over with __syncwarp only -- no CTA
 // barrier after the weight load.  Inside a tile every lane owns a 4-point x 4-unit
@@ -57,8 +61,7 @@ __device__ __forceinline__ float act_bwd(int a, float h) {
 }
 
 struct SmemPlan {
-  int wf[BORE_MAX_LAYERS];   // forward weights  [in4][outP]
-  int wb[BORE_MAX_LAYERS];   // reverse weights  [out4][inP]
+  int wf[BORE_MAX_LAYERS];   // weights [inP][outP + 4] (rows >= in and columns >= out are zero)
   int bias[BORE_MAX_LAYERS]; // [outP]
   int wl;                    // final layer vector, padded
   int weights_total;         // floats
@@ -74,9 +77,9 @@ __host__ __device__ inline void make_plan(const MlpDesc &d, bool grad, int CH, i
   const int G = d.n_layers - 1;  // GEMM (hidden) layers
   for (int l = 0; l < G; ++l) {
     int in = d.dims[l], out = d.dims[l + 1];
-    p.wf[l] = off; off += rup(in, 4) * rup(out, CH);
+    // the reverse pass walks the rows of a whole chunk of input units: rows up to rup(in, CH)
+    p.wf[l] = off; off += (grad ? rup(in, CH) : rup(in, 4)) * (rup(out, CH) + 4);
     p.bias[l] = off; off += rup(out, CH);
-    p.wb[l] = off; if (grad) off += rup(out, 4) * rup(in, CH);
   }
   p.wl_len = G > 0 ? rup(d.dims[G], CH) : rup(d.dims[0], CH / 4);
   p.wl = off; off += p.wl_len;
@@ -111,6 +114,32 @@ __device__ __forceinline__ void tile_gemm(const float *__restrict__ A, const flo
   }
 }
 
+// Reverse pass on the forward image: acc[i][u] += sum_j A[j][pg*4+i] * W[row0 + u*RS][j],  j < J4
+// (multiple of 4), in ascending j -- the same order and the same roundings as a k-loop over a
+// transposed copy.  RS = lanes across units: unit u of this lane is row row0 + u*RS.
+template <int AST, int RS>
+__device__ __forceinline__ void tile_gemm_T(const float *__restrict__ A, const float *__restrict__ Wrow,
+                                            int J4, int ldw, float (&acc)[4][4]) {
+#pragma unroll 2
+  for (int j = 0; j < J4; j += 4) {
+    float4 a[4], w[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) a[jj] = *reinterpret_cast<const float4 *>(A + (j + jj) * AST);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) w[u] = *reinterpret_cast<const float4 *>(Wrow + u * RS * ldw + j);
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const float av[4] = {a[jj].x, a[jj].y, a[jj].z, a[jj].w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float wv = jj == 0 ? w[u].x : jj == 1 ? w[u].y : jj == 2 ? w[u].z : w[u].w;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i][u] = fmaf(av[i], wv, acc[i][u]);
+      }
+    }
+  }
+}
+
 // Writes one model's zero-padded weight image (the shared-memory plan of mlp_eval_kernel) to
 // global memory: grid = models, launched once per parameter change instead of re-deriving the
 // image in every CTA of every launch.
@@ -123,23 +152,15 @@ mlp_pack_kernel(const MlpDesc d, const SmemPlan P, int CH, int grad, const float
   const int tid = threadIdx.x, nthr = blockDim.x;
   for (int l = 0; l < G; ++l) {
     const int in = d.dims[l], outd = d.dims[l + 1];
-    const int in4 = rup(in, 4), outP = rup(outd, CH);
+    const int rows = grad ? rup(in, CH) : rup(in, 4), outP = rup(outd, CH), ld = outP + 4;
     const float *Wg = params + d.w_off[l];
     float *wf = out + P.wf[l];
-    for (int e = tid; e < in4 * outP; e += nthr) {
-      const int k = e / outP, j = e - k * outP;
+    for (int e = tid; e < rows * ld; e += nthr) {
+      const int k = e / ld, j = e - k * ld;
       wf[e] = (k < in && j < outd) ? Wg[k * outd + j] : 0.f;
     }
     float *bs = out + P.bias[l];
     for (int e = tid; e < outP; e += nthr) bs[e] = e < outd ? params[d.b_off[l] + e] : 0.f;
-    if (grad) {
-      const int out4 = rup(outd, 4), inP = rup(in, CH);
-      float *wb = out + P.wb[l];
-      for (int e = tid; e < out4 * inP; e += nthr) {
-        const int j = e / inP, k = e - j * inP;
-        wb[e] = (k < in && j < outd) ? Wg[k * outd + j] : 0.f;
-      }
-    }
   }
   {
     const int in = d.dims[G];
@@ -273,7 +294,7 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
       const int a = d.act[l];
       for (int c = 0; c < outP; c += CH) {
         float acc[4][4] = {};
-        tile_gemm<AST>(A, W + c + ug * 4, in4, outP, acc);
+        tile_gemm<AST>(A, W + c + ug * 4, in4, outP + 4, acc);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int unit = c + ug * 4 + u;
@@ -359,18 +380,19 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
     }
     __syncwarp();
     for (int l = G - 1; l >= 0; --l) {
-      const int out4 = rup(d.dims[l + 1], 4), inP = rup(d.dims[l], CH);
+      const int out4 = rup(d.dims[l + 1], 4), inP = rup(d.dims[l], CH), ldw = rup(d.dims[l + 1], CH) + 4;
       const float *A = strip + P.buf[l + 1] + pg * 4;   // delta_out [j][p]
-      const float *W = smem + P.wb[l];                  // WT [j][k]
+      const float *W = smem + P.wf[l];                  // W [k][j]: rows = this layer's input units
       float *Hin = strip + P.buf[l];
+      // this lane's units of a chunk: c + ug + UG*u (see the header: consecutive rows per quarter-warp)
       if (l > 0) {
         const int a = d.act[l - 1];
         for (int c = 0; c < inP; c += CH) {
           float acc[4][4] = {};
-          tile_gemm<AST>(A, W + c + ug * 4, out4, inP, acc);
+          tile_gemm_T<AST, UG>(A, W + (c + ug) * ldw, out4, ldw, acc);
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            float *hp = Hin + (c + ug * 4 + u) * AST + pg * 4;
+            float *hp = Hin + (c + ug + UG * u) * AST + pg * 4;
             float4 hv = *reinterpret_cast<const float4 *>(hp);
             hv.x = acc[0][u] * act_bwd(a, hv.x);
             hv.y = acc[1][u] * act_bwd(a, hv.y);
@@ -384,10 +406,10 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
         // input gradient: stage through buf0 (x is dead) so the global store is coalesced
         for (int c = 0; c < inP; c += CH) {
           float acc[4][4] = {};
-          tile_gemm<AST>(A, W + c + ug * 4, out4, inP, acc);
+          tile_gemm_T<AST, UG>(A, W + (c + ug) * ldw, out4, ldw, acc);
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int k = c + ug * 4 + u;
+            const int k = c + ug + UG * u;
             if (k < rup(D, 4))
               *reinterpret_cast<float4 *>(Hin + k * AST + pg * 4) =
                   make_float4(acc[0][u], acc[1][u], acc[2][u], acc[3][u]);
