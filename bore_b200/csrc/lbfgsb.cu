@@ -265,10 +265,11 @@ struct BlockMem {
   }
 };
 
-// CTA header in dynamic shared memory: formk output map | lo | hi | nbd | two mbarriers per warp
+// CTA header in dynamic shared memory: formk output map | lo | hi | nbd | two mbarriers per warp |
+// two ints of the K-of-N rendezvous
 __host__ __device__ inline size_t lb_header_bytes(int n, int wpb) {
   return align_up(LB_FORMK_ACC * 32 * sizeof(int), 16) + 2 * align_up(n * sizeof(double), 16) +
-         align_up(n * sizeof(int), 16) + align_up(2 * wpb * sizeof(uint64_t), 16);
+         align_up(n * sizeof(int), 16) + align_up(2 * wpb * sizeof(uint64_t) + 2 * sizeof(int), 16);
 }
 
 // One round.  Work items (positions of the round's active list) are claimed dynamically from a
@@ -279,7 +280,7 @@ __host__ __device__ inline size_t lb_header_bytes(int n, int wpb) {
 // between CTA barriers -- ~10^4 instructions that the warps now fetch together instead of each
 // thrashing the instruction caches from a different place (profiles/r01_notes.md).
 template <typename FG, int MC>
-__global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t warp_bytes, int nphase) {
+__global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t warp_bytes, int nphase, int kofn, int pf) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int n = D.P.n, m = D.P.m;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -306,6 +307,14 @@ __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t w
   const uint32_t p1_bytes = (uint32_t)(SCAL_BYTES + 4 * LB_NV(n) * sizeof(double));
   const uint32_t p2_bytes = block_bytes - p1_bytes;
 
+  // K-of-N rendezvous (kofn > 0): the heavy stage starts as soon as ANY kofn warps of the CTA hold a
+  // heavy item (named barrier 1 with a thread count), instead of waiting for the slowest of all of
+  // them; warps that have run out of work keep feeding arrivals while somebody still waits.
+  // (the two counters live behind the mbarriers in the CTA header: the kernel opts in to ALL of the
+  // dynamic shared memory, which leaves no room for a static allocation)
+  int &kn_wait = reinterpret_cast<int *>(bars + 2 * wpb)[0];
+  int &kn_done = reinterpret_cast<int *>(bars + 2 * wpb)[1];
+  if (threadIdx.x == 0) { kn_wait = 0; kn_done = 0; }
   // claim a position of the active list (>= n_active: the list is exhausted)
   auto claim = [&]() {
     int v = 0;
@@ -315,6 +324,7 @@ __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t w
   // cur_i: the item whose block is staged (or on its way) in this warp's workspace;
   // nxt_i: the one after it, already claimed and prefetched into L2
   int cur_i = claim();
+  int nxt_sid = -1;  // start id of the item claimed ahead (loaded with the claim)
   if (lane == 0) {
     mbar_init(bar, 1);
     mbar_init(bar2, 1);
@@ -410,11 +420,24 @@ __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t w
     bool holding = false;
 #pragma unroll 1
     while (cur_i < n_active) {
-      sid = list_cur[cur_i];
-      // claim the item after this one and pull its block into L2 meanwhile
+      // (the id of this item came with the claim of the previous iteration, see below)
+      sid = nxt_sid >= 0 ? nxt_sid : list_cur[cur_i];
+      // claim the item after this one and pull what its light stage reads into L2 meanwhile: the
+      // head of its block, its request x, and the g / f rows K2 wrote -- 0.9 GB of blocks stream
+      // through the 126 MB L2 every round, so none of them would still be there
       nxt_i = claim();
-      if (lane == 0 && nxt_i < n_active)
-        bulk_prefetch_l2(D.blocks + D.block_stride * list_cur[nxt_i], p1_bytes);
+      nxt_sid = nxt_i < n_active ? list_cur[nxt_i] : -1;
+      if (nxt_sid >= 0 && lane == 0) bulk_prefetch_l2(D.blocks + D.block_stride * nxt_sid, p1_bytes);
+      if (nxt_sid >= 0 && pf) {
+        const char *px = reinterpret_cast<const char *>(D.xreq + (size_t)nxt_sid * n);
+        const char *pg = reinterpret_cast<const char *>(G + (size_t)nxt_sid * n);
+        const int xb = n * (int)sizeof(double), gb = n * (int)sizeof(FG);
+        const char *p = nullptr;
+        if (lane < 16) { if (lane * 128 < xb) p = px + lane * 128; }
+        else if (lane < 31) { if ((lane - 16) * 128 < gb) p = pg + (lane - 16) * 128; }
+        else p = reinterpret_cast<const char *>(F + nxt_sid);
+        if (p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+      }
       const double *xr = D.xreq + (size_t)sid * n;
       const FG *gr = G + (size_t)sid * n;
       const double fval = (double)F[sid];
@@ -455,6 +478,16 @@ __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t w
       finish(r);
       continue;
     }
+    if (kofn > 0) {
+      if (!holding) break;  // the list is exhausted and nothing is in hand
+      if (lane == 0) atomicAdd(&kn_wait, 1);
+      __syncwarp();
+      asm volatile("bar.sync 1, %0;" ::"r"(kofn * 32) : "memory");
+      if (lane == 0) atomicSub(&kn_wait, 1);
+      const int r = LbCore<MC>::advance(P, w, s, mem, 2);
+      finish(r);
+      continue;
+    }
     if (!__syncthreads_or(holding ? 1 : 0)) break;
     // ---- heavy stage, phase-aligned across the CTA ----
     if (holding) {
@@ -471,6 +504,23 @@ __global__ void __maxnreg__(168) lbfgsb_warp_kernel(LbDev D, int round, size_t w
     atomicAdd(D.bytes, my_bytes);
     atomicAdd(D.evals, my_evals);
     bulk_wait_all();
+  }
+  if (kofn > 0) {
+    // out of work: feed the barrier while a warp of this CTA still waits for its group
+    if (lane == 0) atomicAdd(&kn_done, 1);
+#pragma unroll 1
+    for (;;) {
+      int done = 0, waiting = 0;
+      if (lane == 0) {
+        done = *reinterpret_cast<volatile int *>(&kn_done);
+        waiting = *reinterpret_cast<volatile int *>(&kn_wait);
+      }
+      done = __shfl_sync(0xffffffffu, done, 0);
+      waiting = __shfl_sync(0xffffffffu, waiting, 0);
+      if (done >= wpb) break;
+      if (waiting > 0) asm volatile("bar.arrive 1, %0;" ::"r"(kofn * 32) : "memory");
+      __nanosleep(200);
+    }
   }
 }
 
@@ -608,7 +658,20 @@ int launch_round_mc(const LbDev &D, const StepLaunch &SL, int round, int nphase,
                                    227 * 1024));
     if (dev < 64) attr_done[dev] = true;
   }
-  lbfgsb_warp_kernel<FG, MC><<<SL.grid, SL.block, SL.smem, stream>>>(D, round, SL.warp_bytes, nphase);
+  static int kofn = -1;
+  if (kofn < 0) {
+    const char *e = getenv("BORE_LB_KOFN");
+    kofn = e ? atoi(e) : 0;
+    if (kofn < 0) kofn = 0;
+  }
+  // (a group cannot be larger than the CTA; extra phase barriers and K-of-N do not mix)
+  const int k_eff = (nphase == 0 && kofn > 0) ? std::min(kofn, SL.block / 32) : 0;
+  static int pf = -1;
+  if (pf < 0) {
+    const char *e = getenv("BORE_LB_PREFETCH");
+    pf = e ? atoi(e) : 1;
+  }
+  lbfgsb_warp_kernel<FG, MC><<<SL.grid, SL.block, SL.smem, stream>>>(D, round, SL.warp_bytes, nphase, k_eff, pf);
   BORE_CUDA(cudaGetLastError());
   return 0;
 }
