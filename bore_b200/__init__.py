@@ -10,7 +10,8 @@ from .ops import identity, sigmoid, exp, TRANSFORMS  # noqa: F401
 from .base import convert, maybe_distort, maybe_distort_batch, truncated_normal  # noqa: F401
 from .models import (Sequential, DenseSequential, MaximizableModel,  # noqa: F401
                      MaximizableSequential, MaximizableDenseSequential, BatchMaximizableModel,
-                     BatchMaximizableSequential, BatchMaximizableDenseSequential)
-from .data import Record  # noqa: F401
+                     BatchMaximizableSequential, BatchMaximizableDenseSequential,
+                     StackedRecurrentFactory)
+from .data import Record, MultiFidelityRecord  # noqa: F401
 from .math import steps_per_epoch, ceil_divide  # noqa: F401
 from .batched import BatchedMaximizableSequential, problem_shard  # noqa: F401

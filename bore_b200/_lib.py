@@ -77,6 +77,19 @@ SIGNATURES = {
                                  C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                  vp, vp, C.c_int, vp]),
     "bore_svgd_kernel_value_and_grad": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, vp, vp, C.c_int, vp]),
+    "bore_lstm_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    "bore_lstm_destroy": (C.c_int, [vp]),
+    "bore_lstm_num_params": (C.c_int, [vp]),
+    "bore_lstm_set_weights": (C.c_int, [vp, vp]),
+    "bore_lstm_get_weights": (C.c_int, [vp, vp]),
+    "bore_lstm_set_adam_state": (C.c_int, [vp, vp, vp, C.c_int64]),
+    "bore_lstm_get_adam_state": (C.c_int, [vp, vp, vp, C.POINTER(C.c_int64)]),
+    "bore_lstm_set_regularizers": (C.c_int, [vp, vp]),
+    "bore_lstm_predict_sequences": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp]),
+    "bore_lstm_predict": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp]),
+    "bore_lstm_value_and_grad": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, vp]),
+    "bore_lstm_fit": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, vp, vp, vp]),
+    "bore_lstm_evaluate": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_float, vp, vp]),
     "bore_bench_ffma_peak": (C.c_int, [C.c_int, C.c_int, c_double_p]),
 }
 

@@ -6,8 +6,8 @@ small container of ``Dense`` specs that lowers onto a native ``bore_mlp`` handle
 fused CUDA fit kernel, inference the fused forward kernel.  Build-only extensions needed for
 parity testing: ``fit(..., permutations=...)`` and ``get/set_optimizer_state``.
 
-Out of scope: ``BatchMaximizable*`` (SVGD) and ``StackedRecurrentFactory``
-(LSTM multi-fidelity), bore/models.py:36-104.
+``StackedRecurrentFactory`` (the LSTM multi-fidelity classifier, bore/models.py:48-104) lives in
+``bore_b200.recurrent`` and is re-exported here under the reference's module path.
 """
 import numpy as np
 
@@ -263,3 +263,6 @@ class BatchMaximizableSequential(BatchMaximizableMixin, Sequential):
 
 class BatchMaximizableDenseSequential(BatchMaximizableMixin, DenseSequential):
     pass
+
+
+from .recurrent import StackedRecurrentFactory, LSTMCell  # noqa: E402,F401  (bore/models.py:48-104)

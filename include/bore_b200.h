@@ -302,6 +302,48 @@ int bore_svgd_step(double *x_dev, int n_problems, int n, int D, const void *f_de
 int bore_svgd_kernel_value_and_grad(const double *x_dev, int n, int D, double length_scale,
                                     double *K_dev, double *Kgrad_dev, int device, void *stream);
 
+/* ---- K7: LSTM multi-fidelity classifier --------------------
+ * Replaces the Keras networks of StackedRecurrentFactory (bore/models.py:48-104): `num_layers`
+ * LSTMCell(units, activation) + Dense(1).  Parameters in Keras get_weights() order
+ * [K_0 (in,4U), R_0 (U,4U), b_0 (4U), K_1, R_1, b_1, ..., W_dense (U,1), b_dense (1)], gate order
+ * i, f, c, o, recurrent activation sigmoid.  Limits: input_dim <= 32, units <= 32, layers <= 4,
+ * steps <= 8, batch <= 64.
+ *   bore_lstm_predict_sequences  the many-to-many network (Masking -> RNN... -> TimeDistributed
+ *       Dense): X_dev [S][T][D] -> logits out_dev [S][T]; steps whose features ALL equal mask_value
+ *       are masked when use_mask != 0 (state and output carried over, keras.backend.rnn).
+ *   bore_lstm_predict            the one-to-one network build_one_to_one(num_steps)
+ *       (RepeatVector -> same cells -> same Dense on the last step): X_dev [S][D] -> out_dev [S].
+ *   bore_lstm_value_and_grad     f = T(+-u(x)), g = df/dx of the one-to-one network -- the convert()
+ *       closure (bore/base.py:35-42) that bore_lbfgsb_step is fed with; flags_dev (may be NULL)
+ *       selects the rows to evaluate (the stepper's pending flags); X_dev is fp32, or fp64 when
+ *       x_is_f64 (the stepper's xreq_dev; rounded to fp32 as Keras casts its input).
+ *   bore_lstm_fit                Model.fit on padded sequences (multi_fidelity.py:198-225): X_dev
+ *       [N][T][D], Y_dev [N][T], adam + BinaryCrossentropy(from_logits=True) with the mask as sample
+ *       weight, divided by batch x steps; perm_dev [epochs][N] int32; loss_dev [epochs].  One launch,
+ *       asynchronous on `stream`.
+ *   bore_lstm_evaluate           Model.evaluate (multi_fidelity.py:226): out_host[0] = masked loss
+ *       (+ l2 terms), out_host[1] = binary accuracy of the LOGIT at 0.5 over the unmasked steps
+ *       (the from_logits quirk; logging only).  Synchronises `stream`.                          */
+typedef struct bore_lstm bore_lstm;
+int bore_lstm_create(int input_dim, int units, int num_layers, int activation, int device, bore_lstm **out);
+int bore_lstm_destroy(bore_lstm *h);
+int bore_lstm_num_params(const bore_lstm *h);
+int bore_lstm_set_weights(bore_lstm *h, const float *params_host);
+int bore_lstm_get_weights(bore_lstm *h, float *params_host);
+int bore_lstm_set_adam_state(bore_lstm *h, const float *m_host, const float *v_host, int64_t iterations);
+int bore_lstm_get_adam_state(bore_lstm *h, float *m_host, float *v_host, int64_t *iterations);
+int bore_lstm_set_regularizers(bore_lstm *h, const float *l2_per_array_host);
+int bore_lstm_predict_sequences(bore_lstm *h, const float *X_dev, int S, int T, float mask_value,
+                                int use_mask, float *out_dev, void *stream);
+int bore_lstm_predict(bore_lstm *h, const float *X_dev, int S, int num_steps, float *out_dev, void *stream);
+int bore_lstm_value_and_grad(bore_lstm *h, int num_steps, int transform, int negate, const void *X_dev,
+                             int x_is_f64, int S, const int32_t *flags_dev, float *f_dev, float *g_dev,
+                             void *stream);
+int bore_lstm_fit(bore_lstm *h, const float *X_dev, const float *Y_dev, int N, int T, float mask_value,
+                  int batch_size, int epochs, const int32_t *perm_dev, float *loss_dev, void *stream);
+int bore_lstm_evaluate(bore_lstm *h, const float *X_dev, const float *Y_dev, int N, int T, float mask_value,
+                       float *out_host, void *stream);
+
 /* ---- measurement helper -----------------------------------------------------------------
  * FP32 FFMA-only microbenchmark (register-resident FMA chains, all SMs): the measured
  * denominator for the FP32 roofline, since MEASURED_PEAKS.json carries only HBM and BF16.

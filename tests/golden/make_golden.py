@@ -236,15 +236,79 @@ def svgd_golden():
     print("svgd_golden.npz written")
 
 
+def multi_fidelity_cases():
+    """Seeded (x, y, budget) streams shaped like Hyperband brackets: every bracket starts some fresh
+    configurations at one of the budgets and promotes the best third upwards; a few (x, b) pairs are
+    re-evaluated (the reference overwrites the per-configuration value and appends to the rung)."""
+    cases = []
+    for seed, D, budgets, n0 in ((0, 3, (1 / 9, 1 / 3, 1.0), 9), (1, 5, (1 / 27, 1 / 9, 1 / 3, 1.0), 12),
+                                 (2, 2, (0.25, 1.0), 6)):
+        rs = np.random.RandomState(seed)
+        stream = []
+        for bracket in range(len(budgets) + 1):
+            start = bracket % len(budgets)
+            xs = [np.round(rs.uniform(size=D), 6) for _ in range(max(n0 // (start + 1), 2))]
+            for b in budgets[start:]:
+                ys = [float(np.sum((x - 0.4) ** 2) + rs.normal() * 0.1 / b) for x in xs]
+                for x, y in zip(xs, ys):
+                    stream.append((x, y, b))
+                keep = max(len(xs) // 3, 1)
+                xs = [xs[i] for i in np.argsort(ys)[:keep]]
+        x, y, b = stream[3]
+        stream.append((x, y + 0.5, b))  # the same configuration at the same budget again
+        cases.append(dict(seed=seed, D=D, gamma=(0.25 if seed != 1 else 1 / 3), stream=stream))
+    return cases
+
+
+def multi_fidelity_golden():
+    """MultiFidelityRecord (bore/data.py:51-261) run by the reference itself on the streams above."""
+    sys.path.insert(0, "/root/reference")
+    from bore.data import MultiFidelityRecord
+    out = dict(numpy_version=np.array(np.__version__),
+               source=np.array("ltiao/bore v1.5.0 bore.data.MultiFidelityRecord imported from /root/reference"))
+    cases = multi_fidelity_cases()
+    out["cases"] = np.arange(len(cases))
+    for ci, c in enumerate(cases):
+        rec = MultiFidelityRecord(gamma=c["gamma"])
+        for x, y, b in c["stream"]:
+            rec.append(x=x, y=y, b=b)
+        k = f"c{ci}/"
+        out[k + "budgets"] = np.array(rec.budgets())
+        out[k + "rung_sizes"] = np.array(rec.rung_sizes())
+        out[k + "size"] = np.array(rec.size())
+        out[k + "num_features"] = np.array(rec.num_features())
+        out[k + "thresholds"] = np.array(rec.thresholds())
+        out[k + "highest_rung"] = np.array([-1 if rec.highest_rung(m) is None else rec.highest_rung(m)
+                                            for m in (1, 3, 5, 8, 100)])
+        for t in range(rec.num_rungs()):
+            out[k + f"labels{t}"] = np.asarray(rec.binary_labels(t))
+        for name, pad in (("m1", -1.0), ("tiny", 1e-9)):
+            X, Y = rec.sequences(pad_value=pad, binary=True)
+            out[k + f"X_{name}"], out[k + f"Y_{name}"] = X, Y
+        Xc, Yc = rec.sequences(pad_value=-1.0, binary=False)
+        out[k + "Y_values"] = Yc
+        rs = np.random.RandomState(100 + ci)
+        F = np.vstack([np.array(key) for key in rec._data])
+        cand = np.vstack([F[::4] * (1 + 3e-6), F[1::4] + 2e-5, rs.uniform(size=(4, c["D"]))])
+        out[k + "cand"] = cand
+        out[k + "dup"] = np.array([rec.is_duplicate(x) for x in cand])
+    np.savez_compressed(os.path.join(HERE, "multi_fidelity_golden.npz"), **out)
+    print("multi_fidelity_golden.npz written")
+
+
 if __name__ == "__main__":
     if "--svgd" in sys.argv:
         svgd_golden()
+        sys.exit(0)
+    if "--multi-fidelity" in sys.argv:
+        multi_fidelity_golden()
         sys.exit(0)
     if "--data-step" in sys.argv:
         data_step_golden()
         sys.exit(0)
     host_golden()
     data_step_golden()
+    multi_fidelity_golden()
     svgd_golden()
     lbfgsb_golden()
     fit_golden()
