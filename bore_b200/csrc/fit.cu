@@ -20,34 +20,11 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "fit_common.cuh"
 
 namespace {
 
 constexpr int FIT_THREADS = 256;
-
-__device__ __forceinline__ float f_act(int a, float v) {
-  switch (a) {
-    case BORE_ACT_RELU: return fmaxf(v, 0.f);
-    case BORE_ACT_ELU: return v > 0.f ? v : expm1f(v);
-    case BORE_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
-    case BORE_ACT_TANH: return tanhf(v);
-    default: return v;
-  }
-}
-__device__ __forceinline__ float f_act_bwd(int a, float h) {
-  switch (a) {
-    case BORE_ACT_RELU: return h > 0.f ? 1.f : 0.f;
-    case BORE_ACT_ELU: return h > 0.f ? 1.f : h + 1.f;
-    case BORE_ACT_SIGMOID: return h * (1.f - h);
-    case BORE_ACT_TANH: return 1.f - h * h;
-    default: return 1.f;
-  }
-}
-__device__ __forceinline__ float stable_sigmoid(float u) {
-  if (u >= 0.f) return 1.f / (1.f + expf(-u));
-  const float e = expf(u);
-  return e / (1.f + e);
-}
 
 struct FitPlan {
   int w[BORE_MAX_LAYERS];    // W_l  [in][JP]          (all Dense layers incl. final)
@@ -134,34 +111,6 @@ struct FitArgs {
   float *loss_out;
   float lr, beta1, beta2, eps;
 };
-
-__device__ __forceinline__ float block_sum(float v, float *red) {
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __syncthreads();
-  if (lane == 0) red[warp] = v;
-  __syncthreads();
-  float t = 0.f;
-  const int nw = blockDim.x >> 5;
-  for (int i = 0; i < nw; ++i) t += red[i];
-  return t;
-}
-
-// Keras-form Adam on one parameter (eps outside the bias correction); returns the new value.
-// sqrt.approx / div.approx (<= 2 ulp each): the IEEE forms cost ~25 instructions per parameter,
-// a fifth of the whole kernel at Dense32 sizes, for digits far below fp32 re-association noise.
-__device__ __forceinline__ float adam_update(float wv, float g, float &m, float &v, float om1, float om2,
-                                             float alpha, float eps) {
-  m += (g - m) * om1;
-  v += (g * g - v) * om2;
-  float r;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
-  return wv - __fdividef(m * alpha, r + eps);
-}
-
-// e / n for 0 <= e < 2^20 through a precomputed reciprocal (inv = 1.f / n): exact, the offset .5
-// keeps the product away from integer boundaries
-__device__ __forceinline__ int fdiv(int e, float inv) { return __float2int_rz(((float)e + 0.5f) * inv); }
 
 // acc[i][u] += sum_k A[k*lda + i] * B[k*ldb + u]: the 4 x 4 register tile of every GEMM below
 __device__ __forceinline__ void tile_fma(const float *__restrict__ ap, int lda, const float *__restrict__ bp,
@@ -1188,6 +1137,23 @@ int bore_mlp_fit(bore_mlp *h, int model0, int count, const float *X_dev, const f
   }
   a.loss_out = loss_out_dev;
   a.lr = h->lr; a.beta1 = h->beta1; a.beta2 = h->beta2; a.eps = h->eps;
+  // Tensor-pipe kernel (fit_mma.cu: 3xTF32 mma.sync GEMMs, one CTA per model) on request only (fit mode 3 or
+  // BORE_FIT_MMA=1): measured SLOWER than both FFMA mappings below on B200 -- the legacy HMMA path gives
+  // 3xTF32 only 1.3x the FFMA peak and every HMMA needs ~14 more instructions for fragments and splits
+  // (cfg 3: 31.6 vs 20.3 ms; 4,096 cfg-4 models: 224 vs 136 ms; DESIGN.md K1t, profiles/r02_notes.md).
+  {
+    static int mma_env = -1;
+    if (mma_env < 0) {
+      const char *e = getenv("BORE_FIT_MMA");
+      mma_env = e ? atoi(e) : 0;
+    }
+    if (h->fit_mode == 3 || (h->fit_mode == 0 && mma_env)) {
+      const int rc = launch_fit_mma(h, model0, count, X_dev, z_dev, N, shared_data, batch_size, epochs, perm_dev,
+                                    shared_perm, loss_out_dev, (cudaStream_t)stream);
+      if (rc != 0) return rc < 0 ? rc : 0;
+      BORE_CHECK(h->fit_mode != 3, "bore_mlp_fit: the tensor-pipe kernel does not take this net / batch size");
+    }
+  }
   // Few models: one thread-block cluster (8 SMs) per model -- the run is latency bound and a
   // single CTA leaves the other 147 SMs idle.  Many models: one CTA each fills the GPU already.
   {
@@ -1237,7 +1203,7 @@ int bore_mlp_fit(bore_mlp *h, int model0, int count, const float *X_dev, const f
 
 int bore_mlp_set_fit_mode(bore_mlp *h, int mode) {
   BORE_CHECK(h != nullptr, "NULL handle");
-  BORE_CHECK(mode >= 0 && mode <= 2, "bore_mlp_set_fit_mode: mode %d outside [0,2]", mode);
+  BORE_CHECK(mode >= 0 && mode <= 3, "bore_mlp_set_fit_mode: mode %d outside [0,3]", mode);
   h->fit_mode = mode;
   return 0;
 }

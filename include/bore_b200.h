@@ -118,8 +118,11 @@ int bore_mlp_fit(bore_mlp *h, int model0, int count, const float *X_dev,
 /* How bore_mlp_fit maps models onto the GPU: 0 = automatic (default), 1 = one CTA per model
  * (throughput mode, many concurrent models), 2 = one 8-CTA thread-block cluster per model
  * (latency mode: the minibatch is split over 8 SMs, gradients meet in distributed shared
- * memory).  Automatic picks 2 while 8 * count <= number of SMs.  Same results up to fp32
- * summation order.                                                                        */
+ * memory), 3 = tensor pipe (one CTA per model, every GEMM of a step as 3xTF32 mma.sync; hidden
+ * widths <= 128, batch <= 64, 1-unit output layer, else an error) -- kept as the measured
+ * answer to "would tensor cores help": slower than 1 and 2 on B200, so never
+ * picked automatically (BORE_FIT_MMA=1 in the environment prefers it).  Automatic picks 2 while
+ * 8 * count <= number of SMs.  Same results up to fp32 summation order.                      */
 int bore_mlp_set_fit_mode(bore_mlp *h, int mode);
 
 /* Keras Model.evaluate -> mean loss and `accuracy` (plugins/hpbandster/base.py:186).

@@ -93,7 +93,7 @@ def oracle_fit():
             np.abs(hist_ref.astype(np.float64) - hist64))
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 def test_full_size_fit_tracks_the_oracle(mode, oracle_fit):
     from bore_b200.engine import NativeMLP
     hist_ref, adam_ref, self_diff, hist64, or32_vs_64 = oracle_fit

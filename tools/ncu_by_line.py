@@ -9,9 +9,13 @@ root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "bore_b200/lib/libbore_b200.so")], cwd=tmp,
                stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-cubin = [f for f in os.listdir(tmp) if "lbfgsb" in f][0]
-sass = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")
-start = [i for i, l in enumerate(sass) if l.startswith(".text.") and kern_key in l][0]
+sass = start = None
+for cubin in sorted(os.listdir(tmp)):  # the cubin that holds the kernel
+    txt = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")
+    hit = [i for i, l in enumerate(txt) if l.startswith(".text.") and kern_key in l]
+    if hit:
+        sass, start = txt, hit[0]
+        break
 cur, off2line, off2op = None, {}, {}
 for l in sass[start + 1:]:
     if l.startswith("//-----"): break
