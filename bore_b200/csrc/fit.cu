@@ -38,6 +38,8 @@ struct FitPlan {
   int zb;                    // labels [BS]
   int red;                   // reduction scratch [32]
   int idx;                   // gathered row indices [BS] (ints)
+  int nk[BORE_MAX_LAYERS], nj[BORE_MAX_LAYERS];  // narrow register tile (rows k x columns j) of layer l's
+                             // weight-gradient pass when 4 x 4 tiles would leave threads idle (0: not used)
   int gs;                    // gradient partials [ks][in*out + out] of the layer in flight
   int total;                 // floats
   int BS;
@@ -49,7 +51,7 @@ __host__ __device__ inline int r4(int a) { return (a + 3) & ~3; }
 // each layer's tiles over all of them); smem_limit: floats available, splits are dropped if the
 // gradient scratch does not fit
 __host__ __device__ inline void make_fit_plan(const MlpDesc &d, int batch, int threads, int smem_limit,
-                                              FitPlan &p) {
+                                              FitPlan &p, int narrow = 1) {
   const int L = d.n_layers;
   int BS = r4(batch) + 4;
   p.BS = BS;
@@ -79,6 +81,19 @@ __host__ __device__ inline void make_fit_plan(const MlpDesc &d, int batch, int t
     int ks = 1;
     while (items * ks * 2 <= threads && ks * 2 <= nchunk && ks < 16) ks *= 2;
     if (out > 1 && ks == 1) ks = 0;  // enough tiles already: direct path
+    p.nk[l] = p.nj[l] = 0;
+    if (out > 1 && ks >= 2 && narrow) {
+      // fewer 4 x 4 tiles than threads: instead of splitting the tiles over the samples (partials through
+      // shared memory, summed again by the Adam pass -- 14 % of the kernel's instructions at Dense32 sizes)
+      // give every thread ONE smaller tile over all samples; its owner applies Adam from registers.
+      // The smallest shape that still has at most one tile per thread.
+      const int shapes[4][2] = {{1, 1}, {2, 1}, {2, 2}, {4, 2}};
+      for (int q = 0; q < 4; ++q) {
+        const int tk = shapes[q][0], tj = shapes[q][1];
+        if (((in + tk - 1) / tk) * ((out + tj - 1) / tj) <= threads) { p.nk[l] = tk; p.nj[l] = tj; break; }
+      }
+      if (p.nk[l]) ks = 0;
+    }
     p.ks[l] = ks;
     const int need = ks * (in * out + out);
     if (need > gmax) gmax = need;
@@ -128,6 +143,41 @@ __device__ __forceinline__ void tile_fma(const float *__restrict__ ap, int lda, 
   }
 }
 
+// One narrow weight-gradient tile over all samples: acc[i][u] = sum_p Hin[k_i][p] DL[j_u][p], k_i = k0 + i
+// (adjacent rows), j_u = j0 + u * jstep (strided: consecutive lanes own consecutive columns, so the delta
+// rows of a warp are consecutive -- conflict-free float4 loads -- and its Adam-slot traffic is coalesced).
+template <int TK, int TJ>
+__device__ __forceinline__ void narrow_tile(const float *__restrict__ Hin, const float *__restrict__ DL, int BS,
+                                            int BP, int k0, int in, int j0, int jstep, int out,
+                                            float (&acc)[8]) {
+  const float *hp[TK], *dp[TJ];
+#pragma unroll
+  for (int i = 0; i < TK; ++i) hp[i] = Hin + min(k0 + i, in - 1) * BS;
+#pragma unroll
+  for (int u = 0; u < TJ; ++u) dp[u] = DL + min(j0 + u * jstep, out - 1) * BS;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+#pragma unroll 2
+  for (int p = 0; p < BP; p += 4) {
+    float4 hv[TK], dv[TJ];
+#pragma unroll
+    for (int i = 0; i < TK; ++i) hv[i] = *reinterpret_cast<const float4 *>(hp[i] + p);
+#pragma unroll
+    for (int u = 0; u < TJ; ++u) dv[u] = *reinterpret_cast<const float4 *>(dp[u] + p);
+#pragma unroll
+    for (int i = 0; i < TK; ++i)
+#pragma unroll
+      for (int u = 0; u < TJ; ++u) {
+        float c = acc[i * TJ + u];
+        c = fmaf(hv[i].x, dv[u].x, c);
+        c = fmaf(hv[i].y, dv[u].y, c);
+        c = fmaf(hv[i].z, dv[u].z, c);
+        c = fmaf(hv[i].w, dv[u].w, c);
+        acc[i * TJ + u] = c;
+      }
+  }
+}
+
 // Phases of one minibatch step (all inside the CTA, barrier between phases):
 //   gather | forward l = 0..L-1 | loss, dL/dlogit | for l = L-1..0: { delta_{l-1} AND the partial
 //   weight gradients of layer l, side by side } , { Adam on layer l }.
@@ -138,7 +188,7 @@ __device__ __forceinline__ void tile_fma(const float *__restrict__ ap, int lda, 
 // use dot-product forms instead of 4x4 tiles padded with zeros.  (The first version gave every
 // 4x4 gradient tile to one thread: with Dense32 layers 64 / 16 / 8 of 128 threads worked while
 // the rest waited at the barrier -- 44 % of all stall samples, profiles/r01_notes.md.)
-__global__ void __launch_bounds__(FIT_THREADS) fit_kernel(const FitArgs a) {
+__global__ void __launch_bounds__(FIT_THREADS, 2) fit_kernel(const FitArgs a) {
   extern __shared__ __align__(16) float sm[];
   const MlpDesc &d = a.d;
   const FitPlan &P = a.P;
@@ -331,6 +381,79 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_kernel(const FitArgs a) {
               }
             }
           }
+        }
+        if (P.nk[l] > 0) {
+          // (2n) one narrow register tile per thread over ALL samples, in the same phase as (1) (both only
+          //      read); after ONE barrier its owner applies Adam straight from registers.  No trailing
+          //      barrier: the next layer's phase reads delta_{l-1} (complete before this barrier) and
+          //      weights that nobody is writing.
+          const int TK = P.nk[l], TJ = P.nj[l];
+          const int tjn = (out + TJ - 1) / TJ, tkn = (in + TK - 1) / TK;
+          const bool has = tid < tjn * tkn;
+          const int tk = has ? tid / tjn : 0, tj = has ? tid - tk * tjn : 0;
+          const int k0 = tk * TK;
+          float acc[8], am[8], av[8];
+          if (has) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              am[q] = 0.f; av[q] = 0.f;
+              const int i = q / TJ, u = q - i * TJ;  // (TJ is 1 or 2)
+              if (q < TK * TJ) {
+                const int gi = d.w_off[l] + min(k0 + i, in - 1) * out + min(tj + u * tjn, out - 1);
+                am[q] = __ldcg(gm + gi);
+                av[q] = __ldcg(gv + gi);
+              }
+            }
+            if (TK == 4) narrow_tile<4, 2>(Hin, DL, BS, BP, k0, in, tj, tjn, out, acc);
+            else if (TJ == 2) narrow_tile<2, 2>(Hin, DL, BS, BP, k0, in, tj, tjn, out, acc);
+            else if (TK == 2) narrow_tile<2, 1>(Hin, DL, BS, BP, k0, in, tj, tjn, out, acc);
+            else narrow_tile<1, 1>(Hin, DL, BS, BP, k0, in, tj, tjn, out, acc);
+          }
+          // bias gradient db_j = sum_p delta_l[j][p] by the LAST threads (the first ones own the tiles)
+          const int jb = NT - 1 - tid;
+          float gb = 0.f, bm = 0.f, bvv = 0.f;
+          if (jb < out) {
+            bm = __ldcg(gm + d.b_off[l] + jb);
+            bvv = __ldcg(gv + d.b_off[l] + jb);
+            for (int p = 0; p < BP; p += 4) {
+              const float4 dv = *reinterpret_cast<const float4 *>(DL + jb * BS + p);
+              gb += (dv.x + dv.y) + (dv.z + dv.w);
+            }
+          }
+          __syncthreads();  // every read of W_l / W_l^T / delta_l of this phase is done
+          {
+            float *W = sm + P.w[l];
+            float *WT = sm + P.wt[l];
+            const float l2k = a.l2k[l], l2b = a.l2b[l];
+            if (has) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const int i = q / TJ, u = q - i * TJ;
+                const int k = k0 + i, j = tj + u * tjn;
+                if (q < TK * TJ && k < in && j < out) {
+                  const int gi = d.w_off[l] + k * out + j;
+                  float wv = W[k * JP + j];
+                  float g = acc[q];
+                  if (l2k != 0.f) { reg += l2k * wv * wv; g += 2.f * l2k * wv; }
+                  float m = am[q], v = av[q];
+                  wv = adam_update(wv, g, m, v, om1, om2, alpha, a.eps);
+                  gm[gi] = m; gv[gi] = v;
+                  W[k * JP + j] = wv;
+                  if (l > 0) WT[j * KP + k] = wv;
+                }
+              }
+            }
+            if (jb < out) {
+              const int gi = d.b_off[l] + jb;
+              float bv = sm[P.b[l] + jb];
+              if (l2b != 0.f) { reg += l2b * bv * bv; gb += 2.f * l2b * bv; }
+              bv = adam_update(bv, gb, bm, bvv, om1, om2, alpha, a.eps);
+              gm[gi] = bm; gv[gi] = bvv;
+              sm[P.b[l] + jb] = bv;
+            }
+          }
+          cur ^= 1;
+          continue;
         }
         if (ks > 0) {
           // (2a) partial gradients of layer l over sample split s, into gs[s][psz] -- same phase as
@@ -1192,7 +1315,14 @@ int bore_mlp_fit(bore_mlp *h, int model0, int count, const float *X_dev, const f
     }
     if (forced == 32 || forced == 64 || forced == 128 || forced == 256) threads = forced;
   }
-  make_fit_plan(a.d, B, threads, 226 * 1024 / (int)sizeof(float), a.P);
+  {
+    static int narrow = -1;
+    if (narrow < 0) {
+      const char *e = getenv("BORE_FIT_NARROW");
+      narrow = e ? atoi(e) : 1;
+    }
+    make_fit_plan(a.d, B, threads, 226 * 1024 / (int)sizeof(float), a.P, narrow);
+  }
   const size_t smem = (size_t)a.P.total * sizeof(float);
   BORE_CHECK(smem <= 227 * 1024, "bore_mlp_fit: model + batch of %d need %zu B of shared memory", B, smem);
   BORE_CUDA(cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

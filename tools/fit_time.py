@@ -44,12 +44,14 @@ if __name__ == "__main__":
     cfg3 = ([50, 64, 64, 64, 1], ["relu", "relu", "relu", "sigmoid"])
     cfg2 = ([6, 32, 32, 1], ["relu", "relu", "sigmoid"])
     cfg5 = ([8, 32, 32, 32, 1], ["elu", "elu", "elu", "linear"])
-    for mode in (2, 3):
-        print("cfg3 1 model, 992 steps, mode", mode, time_fit(*cfg3, 1, 2000, 31, mode), flush=True)
-    for mode in (1, 3):
+    cfg1 = ([2, 16, 16, 1], ["relu", "relu", "sigmoid"])
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "single"):
+        for mode in (2, 3):
+            print("cfg3 1 model, 992 steps, mode", mode, time_fit(*cfg3, 1, 2000, 31, mode), flush=True)
+            print("cfg5 1 model, 1000 steps, mode", mode, time_fit(*cfg5, 1, 500, 125, mode), flush=True)
+    if which in ("all", "many"):
         for M in (148, 512, 1024, 4096):
-            print("cfg4 net", M, "models, 1000 steps, mode", mode, time_fit(*cfg2, M, 500, 125, mode, reps=2), flush=True)
-    for mode in (2, 3):
-        print("cfg5 1 model, 1000 steps, mode", mode, time_fit(*cfg5, 1, 500, 125, mode), flush=True)
-    for nw in (4, 8, 16):
-        os.environ["BORE_FIT_MMA_WARPS"] = str(nw)
+            print("cfg4 net", M, "models, 1000 steps, mode 1", time_fit(*cfg2, M, 500, 125, 1, reps=2), flush=True)
+        print("cfg5 net 512 models, mode 1", time_fit(*cfg5, 512, 500, 125, 1, reps=2), flush=True)
+        print("cfg1 net 1024 models, 400 steps, mode 1", time_fit(*cfg1, 1024, 110, 200, 1, reps=2), flush=True)
