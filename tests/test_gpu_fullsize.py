@@ -93,7 +93,7 @@ def oracle_fit():
             np.abs(hist_ref.astype(np.float64) - hist64))
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("mode", [1, 2])
 def test_full_size_fit_tracks_the_oracle(mode, oracle_fit):
     from bore_b200.engine import NativeMLP
     hist_ref, adam_ref, self_diff, hist64, or32_vs_64 = oracle_fit
@@ -125,6 +125,28 @@ def test_full_size_fit_tracks_the_oracle(mode, oracle_fit):
           "vs fp64 oracle", d_gpu64.max(), "fp32 oracle vs fp64 oracle", or32_vs_64.max())
     assert net.get_adam_state()[2] == adam_ref.t == EPOCHS * (-(-N_OBS // BATCH)) == 992
     assert hist[-1] < hist[0]  # the classifier learned something
+
+
+def test_full_size_tensor_pipe_fit_is_not_fp32(oracle_fit):
+    """Fit mode 3 (3xTF32 mma.sync, csrc/fit_mma.cu) at full size.  Its products carry ~2^-21 relative error
+    instead of fp32's 2^-24, so the amplified rounding noise of the 992-step run shows up EARLIER than in any
+    fp32 run: measured, the trajectory leaves the 1e-4 band at epoch 6 (the FFMA kernels and the fp32 oracle
+    stay inside it until epoch ~18) -- one of the two reasons the kernel is not the default (the other: it is
+    slower).  This test pins that finding: exact start, same optimum, earlier drift."""
+    from bore_b200.engine import NativeMLP
+    hist_ref, adam_ref, self_diff, hist64, or32_vs_64 = oracle_fit
+    X, z, perms = _problem()
+    net = NativeMLP(DIMS, ACTS)
+    net.set_fit_mode(3)
+    net.set_weights(km.init_weights(DIMS, 0))
+    hist = net.fit(X, z, EPOCHS, BATCH, perms)
+    diff = np.abs(hist - hist_ref)
+    assert diff[:4].max() <= LOSS_TOL, diff[:4].max()
+    d_gpu64 = np.abs(hist.astype(np.float64) - hist64)
+    assert d_gpu64.max() <= 5e-2 and hist[-1] < 0.5 * hist[0]
+    print("full-size fit mode 3: first epoch outside 1e-4:", int(np.argmax(diff > LOSS_TOL)) if (diff > LOSS_TOL).any() else None,
+          "max diff vs fp32 oracle", diff.max(), "vs fp64 oracle", d_gpu64.max(), "fp32 oracle vs fp64", or32_vs_64.max())
+    assert net.get_adam_state()[2] == adam_ref.t
 
 
 def test_full_size_feasible_consistent_descending(trained, full_run):

@@ -1,5 +1,5 @@
 """Tiny invocations of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck):
-python tools/sanitize_target.py [k1|k1c|k2|k3|k3f|k3multi|svgd|data|all]"""
+python tools/sanitize_target.py [k1|k1c|k1t|k2|k3|k3f|k3multi|svgd|data|lstm|all]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -41,6 +41,19 @@ if what in ("k1c", "all"):     # one 8-CTA cluster per model
     net = NativeMLP(d3, a3); net.set_weights(glorot(d3, 0)); net.set_fit_mode(2)
     X, z, perms = data(200, 50, 2)
     print("k1c loss", net.fit(X, z, 2, 64, perms))
+if what in ("k1t", "all"):     # tensor-pipe kernel (fit mode 3): 16-warp CTA and the 4-warp form
+    d3, a3 = [50, 64, 64, 64, 1], ["relu", "relu", "relu", "sigmoid"]
+    net = NativeMLP(d3, a3); net.set_weights(glorot(d3, 0)); net.set_fit_mode(3)
+    X, z, perms = data(150, 50, 2)
+    print("k1t loss", net.fit(X, z, 2, 64, perms))
+    os.environ["BORE_FIT_MMA_WARPS"] = "4"
+    net = NativeMLP(dims, acts, n_models=2)
+    for m in range(2): net.set_weights(glorot(dims, m), model=m)
+    net.set_fit_mode(3)
+    X, z, perms = data(150, 6, 2)
+    net.fit_dev(net.to_device(X, np.float32), net.to_device(z.astype(np.float32), np.float32), 150, 64, 2,
+                net.to_device(perms, np.int32), model0=0, count=2)
+    torch.cuda.synchronize(); print("k1t ok")
 if what in ("k2", "all"):
     net = NativeMLP(dims, acts); net.set_weights(glorot(dims, 0))
     f, g = net.value_and_grad(rs.uniform(size=(100, 6)), "identity", True)
@@ -70,3 +83,17 @@ if what in ("data", "all"):
     z = net.quantile_labels_dev(torch.from_numpy(rs.normal(size=(3, 101))).cuda(), 1 / 3)
     k = net.keep_unique_dev(torch.from_numpy(rs.uniform(size=(2, 5, 6))).cuda(), torch.from_numpy(rs.uniform(size=(2, 9, 6))).cuda())
     torch.cuda.synchronize(); print("data ok")
+if what in ("lstm", "all"):    # K7: masked forward, one-to-one value + gradient, fit, evaluate, argmax loop
+    from bore_b200 import ops
+    from bore_b200.layers import BinaryCrossentropy
+    from bore_b200.models import StackedRecurrentFactory
+    fac = StackedRecurrentFactory(5, 1, num_layers=2, num_units=16, layer_kws=dict(activation="elu"), seed=0)
+    Xs = rs.uniform(size=(40, 3, 5)); Ys = (rs.uniform(size=(40, 3, 1)) < 0.4).astype(np.float64)
+    Xs[::3, 2] = -1.0; Ys[::3, 2] = -1.0; Xs[1::5, 0] = -1.0; Ys[1::5, 0] = -1.0
+    net = fac.build_many_to_many(mask_value=-1.0)
+    net.compile(optimizer="adam", loss=BinaryCrossentropy(from_logits=True), metrics=["accuracy"])
+    h = net.fit(Xs, Ys, epochs=2, batch_size=16, verbose=0).history["loss"]
+    ev = net.evaluate(Xs, Ys); p = net.predict(Xs)
+    one = fac.build_one_to_one(3, transform=ops.sigmoid)
+    r = one.argmax([(0.0, 1.0)] * 5, num_starts=6, num_samples=32, print_fn=None, random_state=np.random.RandomState(0))
+    print("lstm ok", h, ev, p.shape, None if r is None else r.fun)
