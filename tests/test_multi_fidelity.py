@@ -101,3 +101,46 @@ def test_generator_host_logic_without_gpu():
         BOREHyperband(cs, retrain=True)
     with pytest.raises(AssertionError):
         BOREHyperband(cs, gamma=1.5)
+
+
+def test_factory_surface_and_limits_without_gpu():
+    """bore/models.py:48-104: constructor asserts, the limits csrc/lstm.cu states, and -- like every other
+    entry point -- no CPU fallback: touching the weights without a CUDA device raises."""
+    import torch
+    from bore_b200 import _lib
+    from bore_b200.layers import BinaryCrossentropy
+    from bore_b200.models import StackedRecurrentFactory
+    fac = StackedRecurrentFactory(4, 1, num_layers=2, num_units=8, layer_kws=dict(activation="elu"))
+    assert fac.input_dim == 4 and len(fac.cells) == 2 and fac.final_layer.units == 1
+    assert fac._l2() == [0.0] * 8
+    with pytest.raises(AssertionError):
+        StackedRecurrentFactory(4, 1, layer_kws=dict(return_sequences=True))
+    with pytest.raises(AssertionError):
+        StackedRecurrentFactory(4, 1, final_layer_kws=dict(activation="sigmoid"))
+    for kw in (dict(input_dim=64), dict(num_units=64), dict(num_layers=5), dict(output_dim=2)):
+        args = dict(input_dim=4, output_dim=1, num_layers=2, num_units=8)
+        args.update(kw)
+        with pytest.raises(NotImplementedError):
+            StackedRecurrentFactory(**args)
+    with pytest.raises(NotImplementedError):
+        fac.build_one_to_one(9)
+    net = fac.build_many_to_many(mask_value=-1.0)
+    with pytest.raises(RuntimeError, match="compile"):
+        net.fit(np.zeros((3, 2, 4)), np.zeros((3, 2, 1)))
+    with pytest.raises(NotImplementedError):
+        net.compile(optimizer="sgd", loss=BinaryCrossentropy(from_logits=True))
+    with pytest.raises(NotImplementedError):
+        net.compile(optimizer="adam", loss=BinaryCrossentropy(from_logits=False))
+    net.compile(optimizer="adam", loss=BinaryCrossentropy(from_logits=True), metrics=["accuracy"])
+    with pytest.raises(NotImplementedError):
+        net.fit(np.zeros((3, 9, 4)), np.zeros((3, 9, 1)))          # more than 8 rungs
+    with pytest.raises(NotImplementedError):
+        net.fit(np.zeros((3, 2, 4)), np.zeros((3, 2, 1)), batch_size=128)
+    lines = []
+    net.summary(print_fn=lines.append)
+    assert any("LSTMCell" in l for l in lines) and any("mask_value=-1.0" in l for l in lines)
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.BoreNativeError):
+            net.fit(np.zeros((3, 2, 4)), np.zeros((3, 2, 1)), verbose=0)
+        with pytest.raises(_lib.BoreNativeError):
+            fac.build_one_to_one(2).predict(np.zeros((1, 4)))
