@@ -207,7 +207,17 @@ def run_reference(args, wl, rank, world):
     w0 = km.init_weights(wl["dims"], 0)
     S_ref = min(wl["starts"], 64 * cores)
     X0 = np.random.RandomState(1).uniform(size=(S_ref, wl["dims"][0]))
-    pool = mp.get_context("fork").Pool(cores) if cores > 1 else None
+    pool = None
+    if cores > 1:
+        # forked workers (NumPy / SciPy only): collect and freeze the parent's objects first so that a
+        # child's garbage collector never runs a destructor that touches CUDA (tests/helpers.py::fork_pool)
+        import gc
+        gc.collect()
+        gc.freeze()
+        try:
+            pool = mp.get_context("fork").Pool(cores)
+        finally:
+            gc.unfreeze()
     for _ in range(args.warmup):
         reference_step(wl, X, z, perms, w0, X0[:cores * 4], pool, cores)
     tf = ta = 0.0

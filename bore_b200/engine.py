@@ -6,6 +6,7 @@ device memory (``torch.empty(..., device="cuda")``), pinned host staging buffers
 CUDA stream.  There is no CPU fallback -- construction fails without a CUDA device.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -59,13 +60,14 @@ class NativeMLP:
         _lib.check(self.lib.bore_mlp_create(len(codes), dims_c, acts_c, self.n_models, self.device,
                                             C.byref(h)))
         self.h = h
+        self._pid = os.getpid()
         self.n_params = self.lib.bore_mlp_num_params(h)
         self.D = self.dims[0]
         self._work = None  # cached L-BFGS-B workspace (torch uint8 tensor)
 
     def __del__(self):
         h, self.h = getattr(self, "h", None), None
-        if h:
+        if h and getattr(self, "_pid", None) == os.getpid():  # (a forked child must not touch CUDA)
             try:
                 self.lib.bore_mlp_destroy(h)
             except Exception:

@@ -16,6 +16,7 @@ handle (csrc/lstm.cu).  Training is one kernel launch; the argmax is the on-devi
 fallback.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -71,11 +72,12 @@ class NativeLSTM:
         _lib.check(self.lib.bore_lstm_create(self.D, self.U, self.L, ACT_CODES[self.activation],
                                              self.device, C.byref(h)))
         self.h = h
+        self._pid = os.getpid()
         self.n_params = self.lib.bore_lstm_num_params(h)
 
     def __del__(self):
         h, self.h = getattr(self, "h", None), None
-        if h:
+        if h and getattr(self, "_pid", None) == os.getpid():  # (a forked child must not touch CUDA)
             try:
                 self.lib.bore_lstm_destroy(h)
             except Exception:

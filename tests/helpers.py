@@ -64,6 +64,33 @@ def reference_self_agreement(weights, acts, X0, bounds, transform, tol, ref=None
     return float(np.mean(np.abs(alt["fun"] - ref["fun"]) <= tol)), ref, alt
 
 
+class fork_pool:
+    """``multiprocessing`` pool of FORKED workers (NumPy / SciPy only) next to a parent that has CUDA
+    initialised.  A forked child must never run a destructor that touches CUDA (torch tensors, events,
+    native handles): if the child's garbage collector finds such objects in an unreachable cycle -- models hold
+    one through their ``convert`` closure -- the CUDA runtime aborts the child and the pool hangs.  So the
+    parent collects its garbage first and FREEZES what is alive (``gc.freeze``: the child's collector never
+    looks at it); the handles additionally ignore ``__del__`` in a process that did not create them."""
+
+    def __init__(self, cores):
+        import gc
+        import multiprocessing as mp
+        gc.collect()
+        gc.freeze()
+        try:
+            self.pool = mp.get_context("fork").Pool(cores)
+        finally:
+            gc.unfreeze()
+
+    def __enter__(self):
+        return self.pool
+
+    def __exit__(self, *exc):
+        self.pool.terminate()
+        self.pool.join()
+        return False
+
+
 def _minimize_chunk(args):
     weights, acts, X0, lo, hi, transform, options = args
     from scipy.optimize import Bounds
@@ -86,6 +113,6 @@ def parallel_minimize_starts(weights, acts, X0, lo, hi, transform, options=dict(
     if cores == 1:
         outs = [_minimize_chunk(j) for j in jobs]
     else:
-        with mp.get_context("fork").Pool(cores) as pool:
+        with fork_pool(cores) as pool:
             outs = pool.map(_minimize_chunk, jobs)
     return {k: np.concatenate([o[k] for o in outs]) for k in outs[0]}

@@ -22,7 +22,7 @@ import numpy as np
 import pytest
 
 from oracle import keras_mlp as km, argmax as am
-from helpers import permuted_units
+from helpers import permuted_units, fork_pool
 
 pytestmark = pytest.mark.gpu
 
@@ -147,7 +147,7 @@ def test_config_parity(name, report):
     X0 = np.random.RandomState(seed + 1).uniform(size=(S_STARTS, n))
     got = net.lbfgsb(X0, 0.0, 1.0, transform=transform)
     cores = max(1, min(os.cpu_count() or 1, 32))
-    with mp.get_context("fork").Pool(cores) as pool:
+    with fork_pool(cores) as pool:
         ref = _reference(w, acts, X0, transform, pool, cores * 2)
         alt = _reference(permuted_units(w), acts, X0, transform, pool, cores * 2)
     agree = np.abs(got["fun"] - ref["fun"]) <= FUN_TOL
@@ -198,7 +198,7 @@ def test_smooth_objective_sample_of_65536(report):
     got = net.lbfgsb(X0, 0.0, 1.0, transform=transform)
     idx = np.random.RandomState(6).choice(S, S_STARTS, replace=False)
     cores = max(1, min(os.cpu_count() or 1, 32))
-    with mp.get_context("fork").Pool(cores) as pool:
+    with fork_pool(cores) as pool:
         ref = _reference(w, acts, X0[idx], transform, pool, cores * 2)
     agree = np.abs(got["fun"][idx] - ref["fun"]) <= FUN_TOL
     assert got["nit"].mean() >= 3.0  # a real optimisation, not a flat objective
