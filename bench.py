@@ -505,6 +505,7 @@ def run_ours(args, wl, rank, local_rank, world):
         line["cfg4"] = cfg4
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(wl, X, z, perms, w0)
+        line["lstm"] = lstm_measure()
     print(json.dumps(line), flush=True)
 
 
@@ -523,6 +524,84 @@ def cpu_baseline(wl, X, z, perms, w0):
             "argmax_evals_per_sec": ev / ta, "adam_steps_per_sec":
                 wl["epochs"] * (-(-wl["N"] // wl["batch"])) / tf,
             "host_cores_available": os.cpu_count()}
+
+
+def lstm_measure(steps=3, with_cpu=True):
+    """SURVEY.md section 8f row 4, measured: one proposal of the LSTM multi-fidelity plugin on a synthetic
+    record -- 400 configurations of an 8-D space over 4 rungs (successive halving: every rung keeps a third),
+    fit for 100 Adam steps (the plugin's num_steps_per_iter), then the 1,024-sample / 5-start argmax on the
+    one-to-one view of rung 2 -- through the public API, host clock.  With `with_cpu` (the cpu_baseline leg)
+    the oracle port (NumPy restatement + SciPy L-BFGS-B, one core) does the same proposal next to it."""
+    import torch
+    from scipy.optimize import Bounds
+    from bore_b200 import ops
+    from bore_b200.layers import BinaryCrossentropy
+    from bore_b200.models import StackedRecurrentFactory
+    D, U, L, T, N, B, mv = 8, 32, 2, 4, 400, 64, -1.0
+    rs = np.random.RandomState(0)
+    X = np.repeat(rs.uniform(size=(N, 1, D)), T, axis=1)
+    Y = (rs.uniform(size=(N, T, 1)) < 1 / 3).astype(np.float64)
+    alive = N
+    for t in range(T):  # configurations beyond the survivors of rung t are padded
+        X[alive:, t] = mv
+        Y[alive:, t] = mv
+        alive = max(alive // 3, 1)
+    epochs = 100 // (-(-N // B))
+    perms = np.stack([rs.permutation(N) for _ in range(epochs)])
+    bounds = Bounds(np.zeros(D), np.ones(D))
+    fac = StackedRecurrentFactory(D, 1, num_layers=L, num_units=U, layer_kws=dict(activation="elu"), seed=1)
+    net = fac.build_many_to_many(mask_value=mv)
+    net.compile(optimizer="adam", loss=BinaryCrossentropy(from_logits=True), metrics=["accuracy"])
+    one = fac.build_one_to_one(3, transform=ops.sigmoid)
+    w0 = net.get_weights()  # Keras-default initialisers drawn by the factory (glorot / orthogonal / forget bias 1)
+
+    def gpu_step():
+        net.set_weights(w0)
+        net.set_optimizer_state([np.zeros_like(a) for a in w0], [np.zeros_like(a) for a in w0], 0)
+        t0 = time.perf_counter()
+        h = net.fit(X, Y, epochs=epochs, batch_size=B, permutations=perms, verbose=0).history["loss"]
+        t1 = time.perf_counter()
+        r = one.argmax(bounds, num_starts=5, num_samples=1024, print_fn=None, random_state=np.random.RandomState(2))
+        torch.cuda.synchronize()
+        return t1 - t0, time.perf_counter() - t1, h, r
+    gpu_step()
+    tf = ta = 0.0
+    for _ in range(steps):
+        a, b, hist, res = gpu_step()
+        tf += a; ta += b
+    rec = {"workload": f"LSTM{U}x{L} (elu) on {N} sequences x {T} rungs of an {D}-D space, {epochs} epochs x "
+                       f"{-(-N // B)} steps, argmax 1,024 samples -> 5 starts at rung 2",
+           "fit_ms": 1e3 * tf / steps, "argmax_ms": 1e3 * ta / steps, "proposals_per_sec": steps / (tf + ta),
+           "argmax_value": float(-res.fun),
+           "bound": "latency (one CTA trains; <= 5 starts optimise)", "timing": "host clock, public API"}
+    if with_cpu:
+        rec.update(lstm_cpu_port(w0, X, Y, epochs, B, perms, mv, bounds, np.array(hist)))
+    return rec
+
+
+def lstm_cpu_port(w0, X, Y, epochs, B, perms, mv, bounds, gpu_hist):
+    """cpu_baseline leg of the LSTM record: the same proposal by the oracle port on one host core."""
+    from scipy.optimize import minimize
+    from oracle import keras_lstm as kl
+    D = X.shape[2]
+    w = [a.copy() for a in w0]
+    t0 = time.perf_counter()
+    h_ref, _ = kl.fit(w, "elu", X, Y, epochs, B, perms, mv)
+    c_fit = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    Xi = np.random.RandomState(2).uniform(size=(1024, D))
+    zi = kl.predict_one_to_one(w, "elu", Xi, 3)[:, 0]
+    ind = np.argpartition(-zi, kth=4)[:5]
+
+    def fn(x):
+        f, g = kl.value_and_input_grad(w, "elu", x[None], 3, "sigmoid", True, np.float32)
+        return float(f[0]), g[0].astype(np.float64)
+    best = min(minimize(fn, x0=Xi[i], jac=True, method="L-BFGS-B", bounds=bounds,
+                        options=dict(maxiter=1000, ftol=1e-9)).fun for i in ind)
+    c_arg = time.perf_counter() - t0
+    return {"loss_vs_oracle_max_abs": float(np.abs(gpu_hist - h_ref).max()), "oracle_argmax_value": float(-best),
+            "cpu_port": {"fit_ms": 1e3 * c_fit, "argmax_ms": 1e3 * c_arg, "cores": 1,
+                         "proposals_per_sec": 1.0 / (c_fit + c_arg), "kind": "port"}}
 
 
 def cfg4_measure(rank, local_rank, world, steps, warm):

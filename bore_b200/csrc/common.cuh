@@ -69,8 +69,8 @@ struct bore_mlp {
   long long *adam_t;   // [n_models]   Keras `iterations`
   float lr, beta1, beta2, eps;  // Adam hyper-parameters
   float l2k[BORE_MAX_LAYERS], l2b[BORE_MAX_LAYERS];  // l2 regularisers per layer
-  int fit_mode;  // 0 auto, 1 one CTA per model (FFMA), 2 one cluster per model (FFMA), 3 tensor pipe
-                 // (bore_mlp_set_fit_mode)
+  int fit_mode;  // 0 auto, 1 one CTA per model (FFMA), 2 one cluster per model, samples split (FFMA), 3 tensor
+                 // pipe, 4 one cluster per model, units split (FFMA2)  (bore_mlp_set_fit_mode)
 };
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -94,3 +94,8 @@ int launch_mlp_eval_multi(const bore_mlp *h, int model0, int n_models, int per_m
 int launch_fit_mma(const bore_mlp *h, int model0, int count, const float *X_dev, const float *z_dev, int N,
                    int shared_data, int batch_size, int epochs, const int32_t *perm_dev, int shared_perm,
                    float *loss_out_dev, cudaStream_t stream);
+// K1u (fit_unit.cu): one cluster per model, hidden units split over the CTAs.  1 launched, 0 shape not
+// taken (caller falls back to the sample-split cluster kernel), < 0 error
+int launch_fit_unit(const bore_mlp *h, int model0, int count, const float *X_dev, const float *z_dev, int N,
+                    int shared_data, int batch_size, int epochs, const int32_t *perm_dev, int shared_perm,
+                    float *loss_out_dev, cudaStream_t stream);

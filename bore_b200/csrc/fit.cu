@@ -1279,6 +1279,21 @@ int bore_mlp_fit(bore_mlp *h, int model0, int count, const float *X_dev, const f
   }
   // Few models: one thread-block cluster (8 SMs) per model -- the run is latency bound and a
   // single CTA leaves the other 147 SMs idle.  Many models: one CTA each fills the GPU already.
+  // First choice: the unit-split cluster kernel (fit_unit.cu, K1u); shapes it does not take (no hidden
+  // layer, batch > 64, shared memory) and BORE_FIT_UNIT=0 go to the sample-split cluster kernel below.
+  {
+    static int unit_env = -1;
+    if (unit_env < 0) {
+      const char *e = getenv("BORE_FIT_UNIT");
+      unit_env = e ? atoi(e) : 1;
+    }
+    if (h->fit_mode == 4 || (h->fit_mode == 0 && unit_env && count * FIT_CLUSTER <= h->sm_count)) {
+      const int rc = launch_fit_unit(h, model0, count, X_dev, z_dev, N, shared_data, batch_size, epochs, perm_dev,
+                                     shared_perm, loss_out_dev, (cudaStream_t)stream);
+      if (rc != 0) return rc < 0 ? rc : 0;
+      BORE_CHECK(h->fit_mode != 4, "bore_mlp_fit: the unit-split cluster kernel does not take this net / batch size");
+    }
+  }
   {
     FitCPlan CP;
     make_fitc_plan(a.d, B, CP);
@@ -1333,7 +1348,7 @@ int bore_mlp_fit(bore_mlp *h, int model0, int count, const float *X_dev, const f
 
 int bore_mlp_set_fit_mode(bore_mlp *h, int mode) {
   BORE_CHECK(h != nullptr, "NULL handle");
-  BORE_CHECK(mode >= 0 && mode <= 3, "bore_mlp_set_fit_mode: mode %d outside [0,3]", mode);
+  BORE_CHECK(mode >= 0 && mode <= 4, "bore_mlp_set_fit_mode: mode %d outside [0,4]", mode);
   h->fit_mode = mode;
   return 0;
 }

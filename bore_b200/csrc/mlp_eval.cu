@@ -27,6 +27,8 @@
 // the warps that fit beside the weights in shared memory.
 #include <algorithm>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -90,10 +92,59 @@ __host__ __device__ inline void make_plan(const MlpDesc &d, bool grad, int CH, i
   p.warp_total = w;
 }
 
+// Packed FP32 FMA (sm_100a SASS FFMA2, PTX fma.rn.f32x2): two independent IEEE fp32 FMAs per lane and
+// instruction -- the same roundings as two fmaf, so results do not change by a bit; what changes is
+// the instruction count of a k-step (2 LDS.128 + 8 FFMA2 instead of 2 LDS.128 + 16 FFMA).  The pair
+// (w, w) is folded by ptxas into the scalar-broadcast operand form (Rb.F32): no MOV is issued.
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void fma2(uint64_t &c, uint64_t a, uint64_t b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ float2 upk2(uint64_t v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+
 // acc[i][u] += sum_k A[k][pg*4+i] * W[k][col0+u],  k < K4 (multiple of 4)
-template <int AST>
+template <int AST, bool F2>
 __device__ __forceinline__ void tile_gemm(const float *__restrict__ A, const float *__restrict__ W,
                                           int K4, int ldw, float (&acc)[4][4]) {
+  if (F2) {
+    uint64_t c2[2][4];  // c2[h][u] = (acc[2h][u], acc[2h+1][u])
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { c2[0][u] = pk2(acc[0][u], acc[1][u]); c2[1][u] = pk2(acc[2][u], acc[3][u]); }
+#pragma unroll 2
+    for (int k = 0; k < K4; k += 4) {
+      float4 a[4], w[4];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        a[kk] = *reinterpret_cast<const float4 *>(A + (k + kk) * AST);
+        w[kk] = *reinterpret_cast<const float4 *>(W + (k + kk) * ldw);
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const uint64_t a01 = pk2(a[kk].x, a[kk].y), a23 = pk2(a[kk].z, a[kk].w);
+        const float wv[4] = {w[kk].x, w[kk].y, w[kk].z, w[kk].w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint64_t ww = pk2(wv[u], wv[u]);
+          fma2(c2[0][u], a01, ww);
+          fma2(c2[1][u], a23, ww);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float2 lo = upk2(c2[0][u]), hi = upk2(c2[1][u]);
+      acc[0][u] = lo.x; acc[1][u] = lo.y; acc[2][u] = hi.x; acc[3][u] = hi.y;
+    }
+    return;
+  }
 #pragma unroll 2
   for (int k = 0; k < K4; k += 4) {
     float4 a[4], w[4];
@@ -117,9 +168,39 @@ __device__ __forceinline__ void tile_gemm(const float *__restrict__ A, const flo
 // Reverse pass on the forward image: acc[i][u] += sum_j A[j][pg*4+i] * W[row0 + u*RS][j],  j < J4
 // (multiple of 4), in ascending j -- the same order and the same roundings as a k-loop over a
 // transposed copy.  RS = lanes across units: unit u of this lane is row row0 + u*RS.
-template <int AST, int RS>
+template <int AST, int RS, bool F2>
 __device__ __forceinline__ void tile_gemm_T(const float *__restrict__ A, const float *__restrict__ Wrow,
                                             int J4, int ldw, float (&acc)[4][4]) {
+  if (F2) {
+    uint64_t c2[2][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { c2[0][u] = pk2(acc[0][u], acc[1][u]); c2[1][u] = pk2(acc[2][u], acc[3][u]); }
+#pragma unroll 2
+    for (int j = 0; j < J4; j += 4) {
+      float4 a[4], w[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) a[jj] = *reinterpret_cast<const float4 *>(A + (j + jj) * AST);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) w[u] = *reinterpret_cast<const float4 *>(Wrow + u * RS * ldw + j);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const uint64_t a01 = pk2(a[jj].x, a[jj].y), a23 = pk2(a[jj].z, a[jj].w);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float wv = jj == 0 ? w[u].x : jj == 1 ? w[u].y : jj == 2 ? w[u].z : w[u].w;
+          const uint64_t ww = pk2(wv, wv);
+          fma2(c2[0][u], a01, ww);
+          fma2(c2[1][u], a23, ww);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float2 lo = upk2(c2[0][u]), hi = upk2(c2[1][u]);
+      acc[0][u] = lo.x; acc[1][u] = lo.y; acc[2][u] = hi.x; acc[3][u] = hi.y;
+    }
+    return;
+  }
 #pragma unroll 2
   for (int j = 0; j < J4; j += 4) {
     float4 a[4], w[4];
@@ -172,7 +253,7 @@ mlp_pack_kernel(const MlpDesc d, const SmemPlan P, int CH, int grad, const float
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <bool GRAD, int UGB>
+template <bool GRAD, int UGB, bool F2>
 __global__ void __launch_bounds__(512)
 mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ params,
                 const float *__restrict__ packed, const float *__restrict__ X,
@@ -294,7 +375,7 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
       const int a = d.act[l];
       for (int c = 0; c < outP; c += CH) {
         float acc[4][4] = {};
-        tile_gemm<AST>(A, W + c + ug * 4, in4, outP + 4, acc);
+        tile_gemm<AST, F2>(A, W + c + ug * 4, in4, outP + 4, acc);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int unit = c + ug * 4 + u;
@@ -389,7 +470,7 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
         const int a = d.act[l - 1];
         for (int c = 0; c < inP; c += CH) {
           float acc[4][4] = {};
-          tile_gemm_T<AST, UG>(A, W + (c + ug) * ldw, out4, ldw, acc);
+          tile_gemm_T<AST, UG, F2>(A, W + (c + ug) * ldw, out4, ldw, acc);
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             float *hp = Hin + (c + ug + UG * u) * AST + pg * 4;
@@ -406,7 +487,7 @@ mlp_eval_kernel(const MlpDesc d, const SmemPlan P, const float *__restrict__ par
         // input gradient: stage through buf0 (x is dead) so the global store is coalesced
         for (int c = 0; c < inP; c += CH) {
           float acc[4][4] = {};
-          tile_gemm_T<AST, UG>(A, W + (c + ug) * ldw, out4, ldw, acc);
+          tile_gemm_T<AST, UG, F2>(A, W + (c + ug) * ldw, out4, ldw, acc);
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int k = c + ug + UG * u;
@@ -491,14 +572,21 @@ static int launch_variant(const bore_mlp *h, const MlpDesc &d, int model0, const
     if (grid > ctas_needed) grid = ctas_needed;
     if (grid < 1) grid = 1;
   }
-  static bool attr_done[64] = {};  // per device: the attribute belongs to the device's context
-  if (h->device >= 64 || !attr_done[h->device]) {
-    BORE_CUDA(cudaFuncSetAttribute(mlp_eval_kernel<GRAD, UGB>,
+  // packed FFMA2 inner loops unless BORE_K2_FFMA2=0 (the scalar-FFMA build stays for A/B timing; the
+  // two give bit-identical results)
+  static const bool f2 = [] { const char *e = getenv("BORE_K2_FFMA2"); return !(e && e[0] == '0'); }();
+  static bool attr_done[2][64] = {};  // per device: the attribute belongs to the device's context
+  if (h->device >= 64 || !attr_done[f2][h->device]) {
+    BORE_CUDA(cudaFuncSetAttribute(f2 ? mlp_eval_kernel<GRAD, UGB, true> : mlp_eval_kernel<GRAD, UGB, false>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 256));
-    if (h->device < 64) attr_done[h->device] = true;
+    if (h->device < 64) attr_done[f2][h->device] = true;
   }
-  mlp_eval_kernel<GRAD, UGB><<<grid, warps * 32, smem, stream>>>(d, P, params, packed, X, S, n_dev, list,
-                                                               f, g, transform, sign, per_model, flags);
+  if (f2)
+    mlp_eval_kernel<GRAD, UGB, true><<<grid, warps * 32, smem, stream>>>(d, P, params, packed, X, S, n_dev, list,
+                                                                       f, g, transform, sign, per_model, flags);
+  else
+    mlp_eval_kernel<GRAD, UGB, false><<<grid, warps * 32, smem, stream>>>(d, P, params, packed, X, S, n_dev, list,
+                                                                        f, g, transform, sign, per_model, flags);
   BORE_CUDA(cudaGetLastError());
   return 0;
 }

@@ -121,8 +121,11 @@ int bore_mlp_fit(bore_mlp *h, int model0, int count, const float *X_dev,
  * memory), 3 = tensor pipe (one CTA per model, every GEMM of a step as 3xTF32 mma.sync; hidden
  * widths <= 128, batch <= 64, 1-unit output layer, else an error) -- kept as the measured
  * answer to "would tensor cores help": slower than 1 and 2 on B200, so never
- * picked automatically (BORE_FIT_MMA=1 in the environment prefers it).  Automatic picks 2 while
- * 8 * count <= number of SMs.  Same results up to fp32 summation order.                      */
+ * picked automatically (BORE_FIT_MMA=1 in the environment prefers it), 4 = one 8-CTA cluster per
+ * model with the hidden UNITS split over the CTAs (every CTA owns a column and a row slice of each
+ * weight matrix, only activations and deltas cross SMs; needs a hidden layer, batch <= 64, else
+ * an error).  Automatic picks 4 (else 2) while 8 * count <= number of SMs; BORE_FIT_UNIT=0 in the
+ * environment skips 4.  Same results up to fp32 summation order.                             */
 int bore_mlp_set_fit_mode(bore_mlp *h, int mode);
 
 /* Keras Model.evaluate -> mean loss and `accuracy` (plugins/hpbandster/base.py:186).

@@ -42,8 +42,10 @@ CASES = [
 
 
 # fit modes (bore_mlp_set_fit_mode): 1 = one CTA per model (FFMA), 2 = one 8-CTA cluster per model (FFMA),
-# 3 = tensor pipe (3xTF32 mma.sync, csrc/fit_mma.cu -- kept as measured evidence, not the default: slower)
-@pytest.mark.parametrize("mode", [1, 2, 3])
+# 3 = tensor pipe (3xTF32 mma.sync, csrc/fit_mma.cu -- kept as measured evidence, not the default: slower),
+# 4 = one 8-CTA cluster per model with the hidden UNITS split over the CTAs (csrc/fit_unit.cu, the default for
+# few models)
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
 @pytest.mark.parametrize("name,N,epochs,batch,l2", CASES)
 def test_fit_loss_trajectory_matches_oracle(name, N, epochs, batch, l2, mode):
     from bore_b200.engine import NativeMLP
@@ -60,6 +62,11 @@ def test_fit_loss_trajectory_matches_oracle(name, N, epochs, batch, l2, mode):
     if mode == 3 and len(dims) == 2:  # no hidden layer: nothing for the tensor pipe, and it says so
         from bore_b200._lib import BoreNativeError
         with pytest.raises(BoreNativeError, match="tensor-pipe kernel does not take"):
+            net.fit(X, z, epochs, batch, perms, l2=l2)
+        return
+    if mode == 4 and len(dims) == 2:  # no hidden layer: no units to split
+        from bore_b200._lib import BoreNativeError
+        with pytest.raises(BoreNativeError, match="unit-split cluster kernel does not take"):
             net.fit(X, z, epochs, batch, perms, l2=l2)
         return
     hist = net.fit(X, z, epochs, batch, perms, l2=l2)

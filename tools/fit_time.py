@@ -47,9 +47,15 @@ if __name__ == "__main__":
     cfg1 = ([2, 16, 16, 1], ["relu", "relu", "sigmoid"])
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which in ("all", "single"):
-        for mode in (2, 3):
+        for mode in (2, 3, 4):
             print("cfg3 1 model, 992 steps, mode", mode, time_fit(*cfg3, 1, 2000, 31, mode), flush=True)
             print("cfg5 1 model, 1000 steps, mode", mode, time_fit(*cfg5, 1, 500, 125, mode), flush=True)
+    if which == "unit":
+        for mode in (2, 4):
+            print("cfg3 1 model, 992 steps, mode", mode, time_fit(*cfg3, 1, 2000, 31, mode), flush=True)
+            print("cfg5 1 model, 1000 steps, mode", mode, time_fit(*cfg5, 1, 500, 125, mode), flush=True)
+            print("cfg2 1 model, 1000 steps, mode", mode, time_fit(*cfg2, 1, 500, 125, mode), flush=True)
+            print("cfg5 net 18 models, 1000 steps, mode", mode, time_fit(*cfg5, 18, 500, 125, mode), flush=True)
     if which in ("all", "many"):
         for M in (148, 512, 1024, 4096):
             print("cfg4 net", M, "models, 1000 steps, mode 1", time_fit(*cfg2, M, 500, 125, 1, reps=2), flush=True)
