@@ -450,7 +450,7 @@ def run_ours(args, wl, rank, local_rank, world):
                             launches_per_step=agg["rounds"] / K, achieved=k2_tflops, peak=peak_ffma,
                             unit="TFLOP/s", frac=k2_tflops / peak_ffma, peak_source=ffma_src,
                             frac_of_nominal=k2_tflops / NOMINAL_FP32_TFLOPS))
-    kernels.append(dict(name="fit_cluster_kernel (K1 fused training, 1 model = one 8-CTA cluster)",
+    kernels.append(dict(name="fit_unit_kernel (K1u fused training, 1 model = one 8-CTA cluster, hidden units split over the CTAs)",
                         bound="latency (8 SMs)", ms_per_step=timers["fit_ms"] / K, share=timers["fit_ms"] / tot,
                         launches_per_step=1, achieved=fit_tflops, peak=peak_ffma * 8 / 148, unit="TFLOP/s",
                         frac=fit_tflops / (peak_ffma * 8 / 148), peak_source="8 SMs' share of the FFMA peak"))

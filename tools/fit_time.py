@@ -50,6 +50,8 @@ if __name__ == "__main__":
         for mode in (2, 3, 4):
             print("cfg3 1 model, 992 steps, mode", mode, time_fit(*cfg3, 1, 2000, 31, mode), flush=True)
             print("cfg5 1 model, 1000 steps, mode", mode, time_fit(*cfg5, 1, 500, 125, mode), flush=True)
+    if which == "trace":
+        print("cfg3 mode 4", time_fit(*cfg3, 1, 2000, 31, 4, reps=1), flush=True)
     if which == "unit":
         for mode in (2, 4):
             print("cfg3 1 model, 992 steps, mode", mode, time_fit(*cfg3, 1, 2000, 31, mode), flush=True)

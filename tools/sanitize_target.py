@@ -1,5 +1,5 @@
 """Tiny invocations of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck):
-python tools/sanitize_target.py [k1|k1c|k1t|k2|k3|k3f|k3multi|svgd|data|lstm|all]"""
+python tools/sanitize_target.py [k1|k1c|k1u|k1t|k2|k3|k3f|k3multi|svgd|data|lstm|all]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -41,6 +41,17 @@ if what in ("k1c", "all"):     # one 8-CTA cluster per model
     net = NativeMLP(d3, a3); net.set_weights(glorot(d3, 0)); net.set_fit_mode(2)
     X, z, perms = data(200, 50, 2)
     print("k1c loss", net.fit(X, z, 2, 64, perms))
+if what in ("k1u", "all"):     # unit-split cluster kernel (fit mode 4): compile-time shape, run-time shape, l2, 2 models
+    d3, a3 = [50, 64, 64, 64, 1], ["relu", "relu", "relu", "sigmoid"]
+    net = NativeMLP(d3, a3); net.set_weights(glorot(d3, 0)); net.set_fit_mode(4)
+    X, z, perms = data(200, 50, 2)
+    print("k1u loss", net.fit(X, z, 2, 64, perms))
+    d5, a5 = [7, 24, 40, 1], ["tanh", "elu", "linear"]  # run-time-shape build, ragged widths, l2 (extra cluster barrier)
+    net = NativeMLP(d5, a5, n_models=2)
+    for m in range(2): net.set_weights(glorot(d5, m), model=m)
+    net.set_fit_mode(4)
+    X, z, perms = data(100, 7, 2)
+    print("k1u generic loss", net.fit(X, z, 2, 32, perms, l2=1e-3))
 if what in ("k1t", "all"):     # tensor-pipe kernel (fit mode 3): 16-warp CTA and the 4-warp form
     d3, a3 = [50, 64, 64, 64, 1], ["relu", "relu", "relu", "sigmoid"]
     net = NativeMLP(d3, a3); net.set_weights(glorot(d3, 0)); net.set_fit_mode(3)
