@@ -91,6 +91,7 @@ SIGNATURES = {
     "bore_lstm_fit": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, vp, vp, vp]),
     "bore_lstm_evaluate": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_float, vp, vp]),
     "bore_bench_ffma_peak": (C.c_int, [C.c_int, C.c_int, c_double_p]),
+    "bore_mt19937_uniform": (C.c_int, [vp, c_int_p, vp, vp, C.c_int, C.c_longlong, vp]),
 }
 
 

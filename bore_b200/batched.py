@@ -220,13 +220,16 @@ class BatchedMaximizableSequential:
         assert dim == self.dims[0]
         M, net = self.n_problems, self._net
         if X_init is None:
+            # the reference's draw, problem after problem, from the caller's generator (same stream, same state
+            # afterwards: bore_b200/hostrng.py), straight into the pinned staging buffer of the upload
             rs = check_random_state(random_state)
-            X_init = rs.uniform(low=low, high=high, size=(M, num_samples, dim))
+            X64, _ = net.uniform_to_device(rs, low, high, M * num_samples, dim)
+            X64 = X64.view(M, num_samples, dim)
         else:
             rs = check_random_state(random_state) if distortion is not None else None
-        X_init = np.asarray(X_init, np.float64)
-        assert X_init.shape == (M, num_samples, dim)
-        X64 = net.to_device(X_init, np.float64)
+            X_init = np.asarray(X_init, np.float64)
+            assert X_init.shape == (M, num_samples, dim)
+            X64 = net.to_device(X_init, np.float64)
         z_init = net.predict_multi_dev(X64.to(torch.float32))
         if num_starts < num_samples:
             ind = net.topk_groups(z_init, num_starts, negate=True)     # (M, k) within-problem

@@ -104,19 +104,10 @@ class NativeMLP:
             o += k
         return out
 
-    def to_device(self, a, dtype):
-        """numpy -> device tensor through a cached pinned staging buffer (page-locking a fresh
-        buffer per call costs more than the copy itself).  A buffer is reused once the event
-        recorded behind its last host-to-device copy has completed.  A dtype change (the float64
-        arrays of the reference's surface -> the kernels' float32) happens in the same pass that
-        fills the staging buffer, not in a temporary of its own."""
+    def _staging(self, nbytes):
+        """A cached pinned staging buffer of at least ``nbytes`` whose last upload has completed:
+        ``[uint8 tensor, event]`` (None if page-locked memory cannot be had)."""
         torch = _torch()
-        a = np.asarray(a)
-        dtype = np.dtype(dtype)
-        tdt = torch.from_numpy(np.empty(0, dtype)).dtype
-        nbytes = a.size * dtype.itemsize
-        if nbytes == 0:
-            return torch.empty(a.shape, dtype=tdt, device=self._tdev())
         pool = self.__dict__.setdefault("_pinned", [])
         best = None
         for ent in pool:
@@ -131,7 +122,7 @@ class NativeMLP:
             try:
                 buf = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
             except RuntimeError:
-                return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).to(self._tdev())
+                return None
             best = [buf, torch.cuda.Event()]
             pool.append(best)
             if len(pool) > 16:  # drop the oldest idle buffer
@@ -139,6 +130,24 @@ class NativeMLP:
                     if ent[1].query():
                         del pool[i]
                         break
+        return best
+
+    def to_device(self, a, dtype):
+        """numpy -> device tensor through a cached pinned staging buffer (page-locking a fresh
+        buffer per call costs more than the copy itself).  A buffer is reused once the event
+        recorded behind its last host-to-device copy has completed.  A dtype change (the float64
+        arrays of the reference's surface -> the kernels' float32) happens in the same pass that
+        fills the staging buffer, not in a temporary of its own."""
+        torch = _torch()
+        a = np.asarray(a)
+        dtype = np.dtype(dtype)
+        tdt = torch.from_numpy(np.empty(0, dtype)).dtype
+        nbytes = a.size * dtype.itemsize
+        if nbytes == 0:
+            return torch.empty(a.shape, dtype=tdt, device=self._tdev())
+        best = self._staging(nbytes)
+        if best is None:
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).to(self._tdev())
         view = best[0][:nbytes].view(tdt).reshape(a.shape)
         if nbytes >= (1 << 22) and a.flags.writeable and a.dtype.kind in "fiub":
             view.copy_(torch.from_numpy(a))  # large arrays: torch converts / copies on all host cores
@@ -147,6 +156,25 @@ class NativeMLP:
         out = view.to(self._tdev(), non_blocking=True)
         best[1].record(torch.cuda.current_stream(self.device))
         return out
+
+    def uniform_to_device(self, random_state, low, high, n, dim):
+        """``random_state.uniform(low, high, size=(n, dim))`` (bore/mixins.py:49: the candidate points of an
+        argmax, drawn on the host from the caller's generator) written straight into the pinned staging
+        buffer of its upload -> ``(float64 device tensor, host view)``.  The host view is valid until the
+        next upload of this size class; callers that keep rows copy them."""
+        from . import hostrng
+        torch = _torch()
+        nbytes = n * dim * 8
+        best = self._staging(nbytes) if nbytes else None
+        if best is None:
+            X = hostrng.uniform(random_state, low, high, n, dim)
+            return self.to_device(X, np.float64), X
+        view = best[0][:nbytes].view(torch.float64).reshape(n, dim)
+        host = view.numpy()
+        hostrng.uniform(random_state, low, high, n, dim, out=host)
+        out = view.to(self._tdev(), non_blocking=True)
+        best[1].record(torch.cuda.current_stream(self.device))
+        return out, host
 
     # ------------------------------------------------------------------ parameters
     def set_weights(self, weights, model=0):

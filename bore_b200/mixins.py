@@ -69,14 +69,15 @@ class MaximizableMixin:
 
         low, high, dim = _bounds_arrays(bounds)
         net = self._engine(dim)
-        # host RNG exactly like the reference (bore/mixins.py:49): fp64 MT19937 uniforms
-        X_init = random_state.uniform(low=low, high=high, size=(num_samples, dim))
-        X64 = net.to_device(X_init, np.float64)
+        # host RNG exactly like the reference (bore/mixins.py:49): fp64 MT19937 uniforms from the caller's
+        # generator -- the same numbers and the same state afterwards (bore_b200/hostrng.py), written straight
+        # into the pinned staging buffer of the upload
+        X64, X_init = net.uniform_to_device(random_state, low, high, num_samples, dim)
         X32 = X64.to(torch.float32)
         z_init = net.predict_dev(X32)  # raw model output, NO transform (bore/mixins.py:50-52)
         if num_starts == 0:
             i = int(net.topk_smallest(z_init, 1, negate=True)[0].item())
-            return X_init, None, i, -float(z_init[i].item())
+            return np.array(X_init, copy=True), None, i, -float(z_init[i].item())
         ind = net.topk_smallest(z_init, num_starts, negate=True)  # k smallest of f_init = -z
         X0 = X64.index_select(0, ind.to(torch.int64)) if num_starts < num_samples else X64
         res = net.lbfgsb_dev(X0, low, high, transform=self._min_transform_name(),

@@ -20,6 +20,7 @@ from scipy.optimize import OptimizeResult
 from sklearn.utils import check_random_state
 
 from .utils import from_bounds
+from .. import hostrng
 from ..engine import lbfgsb_message
 
 
@@ -100,7 +101,7 @@ def multi_start(minimizer_fn=None):
         (low, high), dims = from_bounds(bounds)
         low = np.asarray(low, np.float64)
         high = np.asarray(high, np.float64)
-        X_init = random_state.uniform(low=low, high=high, size=(num_samples, dims))
+        X_init = hostrng.uniform(random_state, low, high, num_samples, dims)  # numpy's stream, faster
 
         values, _ = fn(X_init)  # batched screening call (bore/optimizers/base.py:53)
         ind = np.argsort(np.asarray(values), kind="stable")

@@ -55,7 +55,9 @@ class NativeLSTM:
     # buffer plumbing shared with the MLP engine (it only needs .device / .lib)
     _tdev = NativeMLP._tdev
     _stream = NativeMLP._stream
+    _staging = NativeMLP._staging
     to_device = NativeMLP.to_device
+    uniform_to_device = NativeMLP.uniform_to_device
     topk_smallest = NativeMLP.topk_smallest
     select_best = NativeMLP.select_best
     keep_unique_dev = NativeMLP.keep_unique_dev

@@ -356,6 +356,17 @@ int bore_lstm_evaluate(bore_lstm *h, const float *X_dev, const float *Y_dev, int
  * Returns TFLOP/s in *tflops_out; synchronous.                                          */
 int bore_bench_ffma_peak(int device, int iters, double *tflops_out);
 
+/* ----------------------------------------------------------------------------------------------
+ * Host side of the argmax: the candidate points.
+ * Replaces `random_state.uniform(low=low, high=high, size=(num_samples, dims))` (bore/mixins.py:49) for a
+ * numpy.random.RandomState: the SAME stream (MT19937, 53-bit doubles from two words, low + (high - low) * u)
+ * and the same state afterwards, ~5x faster than numpy's broadcasting path -- at configs[2] the draw of
+ * 65,536 x 50 doubles per BO iteration took longer than the training kernel.  key[624], *pos: the generator
+ * state (RandomState.get_state()[1], [2]), updated on return; low / high: [dim]; out: [n][dim] doubles
+ * (any host memory, e.g. the pinned staging buffer of the upload).  Pure host code, no GPU involved.   */
+int bore_mt19937_uniform(uint32_t *key, int *pos, const double *low, const double *high, int dim,
+                         long long n, double *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,9 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_lbfgsb.py -m gpu -q -x 2>&1 | tail -2
-timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err
-python - <<PY
+timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_e2e.json 2> gpurun_out/bench.err; python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/bench.json').read().strip().splitlines()[-1])
-print(round(d['ms_per_step'],1), [(k['name'][:12],round(k['ms_per_step'],2)) for k in d['kernels']], d['phases']['evals_per_step_per_gpu'], round(d['e2e']['ms_per_step'],1))
+try:
+    d=json.loads(open('gpurun_out/bench_e2e.json').read().strip().splitlines()[-1])
+    print({k:d[k] for k in ('value','ms_per_step','phases')}); print(d['e2e']); print(d.get('strong') and (d['strong']['ms_per_step'], d['strong']['phases'])); c=d.get('cfg4'); print(c and (c['ms_per_step'], c['value'], c['phases_ms_rank0']))
+except Exception as e:
+    print('bench parse failed', e); print(open('gpurun_out/bench.err').read()[-3000:])
 PY
