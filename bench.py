@@ -123,6 +123,8 @@ class ClockSampler:
         self.gpu, self.proc, self.lines = gpu_index, None, []
 
     def start(self):
+        if self.gpu is None:  # ranks other than 0 do not sample: N nvidia-smi loops on one box take turns at a
+            return            # driver-wide lock and stall each other's kernel launches (8 ranks: +16 ms per step)
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu),
                                           "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
@@ -377,7 +379,7 @@ def run_ours(args, wl, rank, local_rank, world):
     # ---- headline: weak scaling, 65,536 starts on every GPU ----
     K, W = args.steps, max(args.warmup, 3)
     step_weak = make_step(X0d, X0f, S, rank * S, S * world)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank if rank == 0 else None)
     sampler.start()  # before the warm-up: nvidia-smi starting up (NVML init) stalls launches -- one step of 198 ms
                      # instead of 125 when it was started right in front of the timed steps
     for _ in range(W):
@@ -665,11 +667,11 @@ def cfg4_measure(rank, local_rank, world, steps, warm):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank if rank == 0 else None)
+    sampler.start()  # (before the warm-up, rank 0 only: see run_ours)
     for _ in range(warm):
         step()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     t0 = time.perf_counter()
     evals = 0
     for _ in range(steps):
