@@ -32,7 +32,7 @@
 // (eight LDS.128 of activations + two of weights per four k, 32 FFMA2), the partial tiles meet in a shared
 // scratch [warp][unit][sample] and 128 threads sum the partials of four outputs each in a fixed tree, apply
 // bias / activation (or act') and store the slice.  One __syncthreads per half; no shuffles.  K is padded
-// to a multiple of 64 with zero weights.  The pass is bound by shared-memory wavefronts and by the latency
+// to a multiple of 16 with zero weights (one trip of four k per warp).  The pass is bound by shared-memory wavefronts and by the latency
 // of its dependent chain, not by issue slots: all 16 warps splitting K cost more (16 partial copies: 32 KB
 // written and read back per pass), 8 warps the same as 4.
 //
@@ -64,7 +64,7 @@ namespace {
 constexpr int FU_C = 8;          // CTAs per cluster (portable maximum)
 constexpr int FU_THREADS = 512;
 constexpr int FU_NW = FU_THREADS / 32;  // warps
-constexpr int FU_KT = 64;          // K is padded to a multiple of this (k per trip of the partial pass: 4 per warp)
+constexpr int FU_KT = 16;          // K is padded to a multiple of this: 4 consecutive k per trip for each of the FU_KS warps
 constexpr int FU_NBAR = 3 * BORE_MAX_LAYERS + 2;
 
 __host__ __device__ constexpr int fu_r2(int a) { return (a + 1) & ~1; }
@@ -232,6 +232,7 @@ __device__ __forceinline__ float2 fu_upk(fu_u64 v) {
 // (~1,050 cycles per pass measured with clock64); with 4 warps x 16 k the loads are 10 LDS.128 per 32 FFMA2
 // and the partials 8 KB each way.
 constexpr int FU_KS = 4;
+static_assert(FU_KT == 4 * FU_KS, "K is padded to one trip of four k per k-split warp");
 __device__ __forceinline__ void fu_partial(const float *__restrict__ A, const float *__restrict__ Wm, int KP, int U,
                                            int SP, int SPP, float inv_nso, float *__restrict__ mine, int warp, int lane) {
   const int nso = SP >> 3, ntile = nso * (U >> 1), half = SP >> 1;
