@@ -869,7 +869,16 @@ int launch_fit_unit(const bore_mlp *h, int model0, int count, const float *X_dev
   FuArgs a;
   a.d = h->desc;
   const int B = batch_size < N ? batch_size : N;
-  if (!make_fu_plan(a.d, B, a.P)) return 0;
+  // compile-time shapes: NH hidden layers of one width (16 / 32 / 64), padded batch 64; BORE_FIT_UNIT_GENERIC=1
+  // forces the run-time-shape build (A/B timing, tests of both).  A smaller batch (the first iterations of a BO
+  // run have fewer than 64 observations) is padded to 64 samples for them: zero rows, zero dL/dlogit.
+  static const bool generic = [] { const char *e = getenv("BORE_FIT_UNIT_GENERIC"); return e && e[0] == '1'; }();
+  const int nh = a.d.n_layers - 1, hw = a.d.n_layers >= 2 ? a.d.dims[1] : 0;
+  bool uniform = a.d.n_layers >= 2;
+  for (int i = 2; i <= nh; ++i) uniform = uniform && a.d.dims[i] == hw;
+  const bool fixed_shape = !generic && uniform && B <= 64 &&
+                           ((nh == 3 && (hw == 64 || hw == 32)) || (nh == 2 && (hw == 32 || hw == 16)));
+  if (!make_fu_plan(a.d, fixed_shape ? 64 : B, a.P)) return 0;
   if (a.P.SP > 64) return 0;  // the loss reduction assumes the samples sit in two warps
   const size_t smem = (size_t)a.P.total * sizeof(float);
   if (smem > 226 * 1024) return 0;
@@ -885,13 +894,7 @@ int launch_fit_unit(const bore_mlp *h, int model0, int count, const float *X_dev
   }
   a.loss_out = loss_out_dev;
   a.lr = h->lr; a.beta1 = h->beta1; a.beta2 = h->beta2; a.eps = h->eps;
-  // compile-time shapes: NH hidden layers of one width (16 / 32 / 64), padded batch 64; BORE_FIT_UNIT_GENERIC=1
-  // forces the run-time-shape build (A/B timing, tests of both)
-  static const bool generic = [] { const char *e = getenv("BORE_FIT_UNIT_GENERIC"); return e && e[0] == '1'; }();
-  const int nh = a.d.n_layers - 1, hw = a.d.dims[1];
-  bool uniform = true;
-  for (int i = 2; i <= nh; ++i) uniform = uniform && a.d.dims[i] == hw;
-  if (!generic && uniform && a.P.SP == 64) {
+  if (fixed_shape) {
     if (nh == 3 && hw == 64) return fu_launch<3, 64, 64>(a, count, smem, stream);
     if (nh == 3 && hw == 32) return fu_launch<3, 32, 64>(a, count, smem, stream);
     if (nh == 2 && hw == 32) return fu_launch<2, 32, 64>(a, count, smem, stream);

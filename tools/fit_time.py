@@ -58,6 +58,7 @@ if __name__ == "__main__":
             print("cfg5 1 model, 1000 steps, mode", mode, time_fit(*cfg5, 1, 500, 125, mode), flush=True)
             print("cfg2 1 model, 1000 steps, mode", mode, time_fit(*cfg2, 1, 500, 125, mode), flush=True)
             print("cfg5 net 18 models, 1000 steps, mode", mode, time_fit(*cfg5, 18, 500, 125, mode), flush=True)
+            print("cfg5 net, 40 observations (small batch), 1000 steps, mode", mode, time_fit(*cfg5, 1, 40, 1000, mode), flush=True)
     if which in ("all", "many"):
         for M in (148, 512, 1024, 4096):
             print("cfg4 net", M, "models, 1000 steps, mode 1", time_fit(*cfg2, M, 500, 125, 1, reps=2), flush=True)
