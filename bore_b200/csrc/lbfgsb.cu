@@ -719,7 +719,13 @@ int check_opts(int S, int D, int m, int maxls) {
 // rendezvous of the round kernel avoids.  Hence by default fused up to FUSED_MAX_STARTS starts,
 // rounds above.  g_lb_mode: -1 from the environment (BORE_LB_FUSED = 0 never / 1 default / 2
 // always fused when it fits), 0 default rule, 1 always rounds, 2 always fused.
-constexpr int FUSED_MAX_STARTS = 16384;
+// Re-measured in the third part of round 2 WITH the tail handover the default rule adds to the rounds (ms, fused vs
+// rounds + handover): cfg-3 net (n = 50) 4,096 starts 13.8 vs 13.3, 6,144: 18.5 vs 17.6, 8,192: 24.1 vs 20.9, 10,240:
+// 29.1 vs 23.8, 16,384: 45.9 vs 33.5; cfg-5 net (n = 8) 4,096: 3.1 vs 3.3, 8,192: 5.7 vs 6.7, 16,384: 10.9 vs 10.6;
+// cfg-2 net (n = 6) 8,192: 7.1 vs 8.0, 16,384: 13.1 vs 13.0.  The heavy stage grows with n and with it the fetch
+// problem of the fused kernel, so the limit is 4,096 starts (= the handover threshold: below it the rounds would
+// hand everything over at once) for n > 16 and 16,384 for small problems.  BORE_LB_FUSED_MAX overrides it.
+constexpr int FUSED_MAX_STARTS = 16384, FUSED_MAX_STARTS_LARGE_N = 4096, FUSED_LARGE_N = 16;
 int g_lb_mode = -1;
 int lb_mode() {
   if (g_lb_mode < 0) {
@@ -733,7 +739,10 @@ bool use_fused(const bore_mlp *h, int S, int m, int per_model) {
   const int mode = lb_mode();
   if (mode == 1) return false;
   // (batched problems: a few starts per model, the rounds never leave their latency floor)
-  if (mode == 0 && per_model == 0 && S > FUSED_MAX_STARTS) return false;
+  static const int fused_max_env = [] { const char *e = getenv("BORE_LB_FUSED_MAX"); return e ? atoi(e) : 0; }();
+  const int fused_max = fused_max_env > 0 ? fused_max_env
+                                          : (h->desc.dims[0] > FUSED_LARGE_N ? FUSED_MAX_STARTS_LARGE_N : FUSED_MAX_STARTS);
+  if (mode == 0 && per_model == 0 && S > fused_max) return false;
   return m <= BORE_LBFGSB_MAXCOR && lbfgsb_fused_fits(h, m) != 0;
 }
 

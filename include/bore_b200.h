@@ -154,7 +154,7 @@ size_t bore_lbfgsb_workspace_bytes(int S, int D, int m);
 size_t bore_lbfgsb_minimize_workspace_bytes(const bore_mlp *h, int S, int m);
 /* How bore_lbfgsb_minimize / _minimize_multi run (process-wide): 0 = default rule -- ONE fused
  * persistent launch (a warp keeps its start in shared memory and evaluates the MLP itself) when
- * the model fits and S <= 16,384, lock-step rounds of K2 + stepper launches above; 1 = always
+ * the model fits and S <= 4,096 (16,384 for problems of at most 16 dimensions), lock-step rounds of K2 + stepper launches above; 1 = always
  * rounds (the path bore_lbfgsb_step exposes); 2 = always fused when the model fits.
  * BORE_LB_FUSED=0 / 1 / 2 in the environment selects 1 / 0 / 2 at start-up.  Query workspace
  * sizes after changing it.                                                                  */

@@ -62,7 +62,7 @@ def test_fused_equals_rounds_other_maxcor(m):
 
 
 def test_default_rule_hands_the_tail_over(monkeypatch):
-    """Above 16,384 starts the default rule runs lock-step rounds and finishes the last few
+    """Above 16,384 starts (4,096 for more than 16 dimensions) the default rule runs lock-step rounds and finishes the last few
     thousand starts with the fused kernel in resume mode: same results as rounds alone."""
     from bore_b200.engine import NativeMLP
     dims, acts, transform = NETS["cfg5_plugin8"]
